@@ -1,0 +1,85 @@
+// Shared internals of libplasticity_b200: context object, error plumbing,
+// launch accounting, reference constants.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "plasticity_b200.h"
+
+struct pb_context {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;   // kernels launched by this library on `stream`
+  // Staging for double<->float conversion at the host boundary.
+  double *stage = nullptr;
+  size_t stage_elems = 0;
+  // Partial-sum workspace for batched weight gradients.
+  float *workspace = nullptr;
+  size_t workspace_elems = 0;
+};
+
+namespace pb {
+
+void set_error(const std::string &msg);
+int fail(const std::string &msg);
+int ensure_stage(pb_context *ctx, size_t elems);
+int ensure_workspace(pb_context *ctx, size_t elems);
+
+// The reference prints NumericValue::e with 6 significant digits
+// (symbolic/numeric_value.cc:41-53), so its kernels compute pow(2.71828, x).
+// pow(2.71828, x) == exp2(x * log2(2.71828)).
+constexpr double kRefE = 2.71828;
+constexpr float kLog2RefE = 1.442694067955017f;     // fl32(log2(2.71828))
+constexpr float kLog2RefE_lo = 2.5012059090556704e-09f;  // log2(2.71828) - hi
+constexpr float kLn2 = 0.6931471805599453f;
+// std::numeric_limits<double>::epsilon() printed the same way
+// (symbolic/symbolic_util.cc:40-42).
+constexpr float kRefEps = 2.22045e-16f;
+
+// pow(2.71828, x) in fp32.  x*log2(2.71828) is split into the rounded product
+// t and its exact residual r (plus the constant's low word), so the result
+// stays accurate to a few ulp for |x| up to the overflow range instead of
+// losing |x|*2^-24 in the exponent:  2^(t+r) = 2^t * (1 + r ln2 + ...).
+__device__ __forceinline__ float ref_exp(float x) {
+  const float t = x * kLog2RefE;
+  const float r = isinf(t) ? 0.0f : fmaf(x, kLog2RefE, -t) + x * kLog2RefE_lo;
+  return exp2f(t) * fmaf(r, kLn2, 1.0f);
+}
+
+}  // namespace pb
+
+#define PB_CUDA(expr)                                                        \
+  do {                                                                       \
+    cudaError_t e__ = (expr);                                                \
+    if (e__ != cudaSuccess)                                                  \
+      return pb::fail(std::string(#expr) + ": " + cudaGetErrorString(e__));  \
+  } while (0)
+
+#define PB_CHECK(cond, msg)                 \
+  do {                                      \
+    if (!(cond)) return pb::fail(msg);      \
+  } while (0)
+
+// After every kernel launch: count it and surface launch-configuration errors.
+#define PB_LAUNCHED(ctx)                                                     \
+  do {                                                                       \
+    (ctx)->launches++;                                                       \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    if (e__ != cudaSuccess)                                                  \
+      return pb::fail(std::string("kernel launch: ") +                       \
+                      cudaGetErrorString(e__));                              \
+  } while (0)
+
+static inline int pb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Grid for a grid-stride elementwise kernel: enough CTAs to fill every SM a
+// few times over, never more than the work needs.
+static inline int pb_ew_grid(const pb_context *ctx, int64_t n, int threads) {
+  int64_t want = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)ctx->num_sms * 8;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}

@@ -1,0 +1,55 @@
+// Internal launch functions shared between translation units.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pb {
+
+// elementwise.cu
+int activation_evaluate(pb_context *ctx, int act, const float *I, float *O, int64_t n);
+int activation_input_delta(pb_context *ctx, int act, const float *I, const float *G,
+                           float *dI, int64_t n);
+int pool_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, float *O,
+                  int64_t batch);
+int pool_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                     const float *G, float *dI, int64_t batch);
+int softmax_evaluate(pb_context *ctx, int64_t n, const float *I, float *O, int64_t batch);
+int softmax_input_delta(pb_context *ctx, int64_t n, const float *I, const float *G,
+                        float *dI, int64_t batch);
+
+// dense.cu
+int dense_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
+                   float *O, int64_t batch);
+int dense_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *W,
+                      const float *G, float *dI, int64_t batch);
+int dense_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                        const float *W, const float *G, float *out, const float *lr,
+                        int mode, int64_t batch);
+
+// conv.cu
+int conv_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
+                  float *O, int64_t batch);
+int conv_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *W,
+                     const float *G, float *dI, int64_t batch);
+int conv_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                       const float *W, const float *G, float *out, const float *lr,
+                       int mode, int64_t batch);
+
+// Output extent of a convolution, nnet/convolution_layer.cc:36-44.
+static inline int64_t conv_out_w(const pb_layer_desc *l) {
+  return (l->width - l->filter_width + 2 * l->padding) / l->stride + 1;
+}
+static inline int64_t conv_out_h(const pb_layer_desc *l) {
+  return (l->height - l->filter_height + 2 * l->padding) / l->stride + 1;
+}
+
+// out = W - lr*g | -lr*g | out - lr*g   (back_prop.kernel.cl:28-44 + combine)
+__device__ __forceinline__ void apply_update(int mode, float *out, const float *W,
+                                             int64_t idx, float lr, float g) {
+  if (mode == PB_NEW_WEIGHTS) out[idx] = W[idx] - lr * g;
+  else if (mode == PB_WEIGHT_DELTAS) out[idx] = -lr * g;
+  else out[idx] += -lr * g;
+}
+
+}  // namespace pb

@@ -1,0 +1,403 @@
+// Network driver: the body of nnet::Nnet (nnet/nnet.h) over the layer
+// launchers.  Evaluate :213-273, Train :369-483, Error :280-314,
+// ErrorGradients :316-349, BatchTrain / CalculateGradients :514-669,
+// SetLearningParameters :357-361, Xavier init nnet/layer.cc:86-100.
+//
+// Device-resident state (fp32): all layers' weights concatenated in layer
+// order (reference layout per layer), a same-shaped delta buffer for
+// gradient-sum training, one activation buffer per layer sized for max_batch
+// samples (the reference's eval_layer_outputs_), two ping-pong gradient
+// buffers (backprop_gradients_ / next_backprop_gradients_) and a 1-element
+// learning-rate buffer (learning_rate_buffer_).
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+struct pb_nnet {
+  pb_context *ctx = nullptr;
+  std::vector<pb_layer_desc> layers;
+  int loss = PB_MEAN_SQUARED;
+  int64_t max_batch = 1;
+  std::vector<int64_t> ni, no, nw, w_off;
+  int64_t total_w = 0, max_io = 0;
+  float *weights = nullptr, *deltas = nullptr;
+  std::vector<float *> outputs;
+  float *grad_a = nullptr, *grad_b = nullptr;
+  float *lr = nullptr;
+  float *err = nullptr;  // n_out loss components
+  // strict per-sample SGD loop (pb_nnet_train_loop)
+  struct Cursor { const float *ins; const float *expected; long long idx; };
+  Cursor *cursor = nullptr;
+  float *stage_in = nullptr, *stage_exp = nullptr;
+  cudaGraphExec_t train_exec = nullptr;
+  uint64_t graph_launches = 0;  // kernels inside one replay of train_exec
+};
+
+namespace pb {
+
+int layer_check(const pb_layer_desc *l);
+
+__global__ void xavier_kernel(float *__restrict__ w, int64_t n, float stddev,
+                              unsigned long long seed, unsigned long long base) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // splitmix64 on (seed, global index) -> two uniforms -> Box-Muller.
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (base + (unsigned long long)i + 1);
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x = x ^ (x >> 31);
+    const float u1 = ((float)(unsigned)(x >> 40) + 1.0f) * (1.0f / 16777217.0f);
+    const float u2 = (float)(unsigned)((x >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+    w[i] = stddev * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  }
+}
+
+// Copies sample `idx` of the resident data set into the fixed staging buffers
+// the captured training graph reads, so the graph needs no per-replay update.
+__global__ void fetch_sample_kernel(const pb_nnet::Cursor *__restrict__ cur,
+                                    float *__restrict__ stage_in,
+                                    float *__restrict__ stage_exp, int nin, int nout) {
+  const float *src = cur->ins + (int64_t)cur->idx * nin;
+  const float *exp = cur->expected + (int64_t)cur->idx * nout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nin + nout;
+       i += gridDim.x * blockDim.x) {
+    if (i < nin) stage_in[i] = src[i];
+    else stage_exp[i - nin] = exp[i - nin];
+  }
+}
+
+__global__ void advance_cursor_kernel(pb_nnet::Cursor *cur) { cur->idx += 1; }
+
+static int forward(pb_nnet *net, const float *d_in, int64_t batch) {
+  const float *cur = d_in;
+  for (size_t l = 0; l < net->layers.size(); ++l) {
+    const float *W = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
+    if (pb_layer_evaluate(net->ctx, &net->layers[l], cur, W, net->outputs[l], batch)) return 1;
+    cur = net->outputs[l];
+  }
+  return 0;
+}
+
+// Reverse loop of Nnet::Train (nnet/nnet.h:399-460).  `g` holds dE/dO of the
+// last layer on entry.  Per layer: input_delta with the pre-update weights,
+// then the weight kernel.  Returns the buffer holding dE/dInput in *g_out.
+static int backward(pb_nnet *net, const float *d_in, int64_t batch, float *g, float *ng,
+                    int mode, bool first_chunk, float **g_out) {
+  for (int l = (int)net->layers.size() - 1; l >= 0; --l) {
+    const pb_layer_desc *L = &net->layers[l];
+    const float *layer_in = (l > 0) ? net->outputs[l - 1] : d_in;
+    float *W = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
+    if (pb_layer_input_delta(net->ctx, L, layer_in, W, g, ng, batch)) return 1;
+    if (net->nw[l] > 0) {
+      // PB_NEW_WEIGHTS updates in place: the weight gradient reads only the
+      // layer's inputs and G, and input_delta (which reads W) is already
+      // queued ahead of it on the in-order stream — the same ordering the
+      // reference gets from DeepClone + handle swap (nnet.h:432-454).
+      float *out = (mode == PB_NEW_WEIGHTS) ? W : net->deltas + net->w_off[l];
+      const int m = (mode == PB_NEW_WEIGHTS) ? PB_NEW_WEIGHTS
+                    : first_chunk            ? PB_WEIGHT_DELTAS
+                                             : PB_ACCUMULATE;
+      if (pb_layer_weight_update(net->ctx, L, layer_in, W, g, out, net->lr, m, batch)) return 1;
+    }
+    float *t = g; g = ng; ng = t;
+  }
+  *g_out = g;
+  return 0;
+}
+
+static int train_step(pb_nnet *net, const float *d_in, const float *d_expected,
+                      float *d_input_gradients, const float *d_initial_gradients) {
+  pb_context *ctx = net->ctx;
+  const int64_t n_out = net->no.back();
+  if (forward(net, d_in, 1)) return 1;
+  if (d_initial_gradients) {
+    if (pb_buffer_copy(ctx, net->grad_a, d_initial_gradients, n_out)) return 1;
+  } else {
+    if (pb_error_gradients(ctx, net->loss, n_out, net->outputs.back(), d_expected,
+                           net->grad_a, 1))
+      return 1;
+  }
+  float *g = nullptr;
+  if (backward(net, d_in, 1, net->grad_a, net->grad_b, PB_NEW_WEIGHTS, true, &g)) return 1;
+  if (d_input_gradients) return pb_buffer_copy(ctx, d_input_gradients, g, net->ni[0]);
+  return 0;
+}
+
+}  // namespace pb
+
+extern "C" {
+
+int pb_nnet_create(pb_context *ctx, const pb_layer_desc *layers, int32_t n_layers,
+                   int32_t loss, int64_t max_batch, pb_nnet **out) {
+  PB_CHECK(ctx && layers && out, "pb_nnet_create: null");
+  PB_CHECK(n_layers > 0, "Invalid dimensions passed to Nnet(): empty architecture");
+  PB_CHECK(loss == PB_MEAN_SQUARED || loss == PB_CROSS_ENTROPY,
+           "Error: Unknown loss function selected.");
+  PB_CHECK(max_batch >= 1, "pb_nnet_create: max_batch must be >= 1");
+  PB_CUDA(cudaSetDevice(ctx->device));
+  pb_nnet *net = new pb_nnet();
+  net->ctx = ctx;
+  net->loss = loss;
+  net->max_batch = max_batch;
+  net->layers.assign(layers, layers + n_layers);
+  for (int l = 0; l < n_layers; ++l) {
+    if (pb::layer_check(&layers[l])) { delete net; return 1; }
+    int64_t a, b, c;
+    pb_layer_num_inputs(&layers[l], &a);
+    pb_layer_num_outputs(&layers[l], &b);
+    pb_layer_num_weights(&layers[l], &c);
+    // Architecture::VerifyArchitecture, nnet/architecture.h:16-32: only the
+    // flat counts of consecutive layers have to agree.
+    if (l > 0 && net->no.back() != a) {
+      delete net;
+      return pb::fail("Dimension mismatch between output of layer " + std::to_string(l - 1) +
+                      " (" + std::to_string(net->no.empty() ? 0 : net->no.back()) +
+                      ") and input of layer " + std::to_string(l) + " (" + std::to_string(a) +
+                      ").");
+    }
+    if (a <= 0 || b <= 0) {
+      delete net;
+      return pb::fail("Layer " + std::to_string(l) + " has zero inputs or outputs");
+    }
+    net->ni.push_back(a);
+    net->no.push_back(b);
+    net->nw.push_back(c);
+    net->w_off.push_back(net->total_w);
+    // Keep every layer's weight block 16-byte aligned inside the flat buffer.
+    net->total_w += (c + 3) & ~int64_t(3);
+    net->max_io = std::max(net->max_io, std::max(a, b));
+  }
+  auto dalloc = [&](float **p, int64_t n) {
+    return cudaMalloc((void **)p, sizeof(float) * (size_t)std::max<int64_t>(n, 4));
+  };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = dalloc(&net->weights, net->total_w);
+  if (e == cudaSuccess) e = dalloc(&net->deltas, net->total_w);
+  if (e == cudaSuccess) e = dalloc(&net->grad_a, net->max_io * max_batch);
+  if (e == cudaSuccess) e = dalloc(&net->grad_b, net->max_io * max_batch);
+  if (e == cudaSuccess) e = dalloc(&net->lr, 4);
+  if (e == cudaSuccess) e = dalloc(&net->err, net->no.back());
+  if (e == cudaSuccess) e = dalloc(&net->stage_in, net->ni[0]);
+  if (e == cudaSuccess) e = dalloc(&net->stage_exp, net->no.back());
+  if (e == cudaSuccess) e = cudaMalloc((void **)&net->cursor, sizeof(pb_nnet::Cursor));
+  net->outputs.assign(n_layers, nullptr);
+  for (int l = 0; l < n_layers && e == cudaSuccess; ++l)
+    e = dalloc(&net->outputs[l], net->no[l] * max_batch);
+  if (e == cudaSuccess)
+    e = cudaMemsetAsync(net->weights, 0, sizeof(float) * (size_t)std::max<int64_t>(net->total_w, 4), ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemsetAsync(net->deltas, 0, sizeof(float) * (size_t)std::max<int64_t>(net->total_w, 4), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(net->lr, 0, 4 * sizeof(float), ctx->stream);
+  if (e != cudaSuccess) {
+    pb_nnet_destroy(net);
+    return pb::fail(std::string("pb_nnet_create: ") + cudaGetErrorString(e));
+  }
+  *out = net;
+  return 0;
+}
+
+int pb_nnet_destroy(pb_nnet *net) {
+  if (!net) return 0;
+  cudaSetDevice(net->ctx->device);
+  cudaStreamSynchronize(net->ctx->stream);
+  if (net->train_exec) cudaGraphExecDestroy(net->train_exec);
+  cudaFree(net->weights); cudaFree(net->deltas);
+  cudaFree(net->grad_a); cudaFree(net->grad_b);
+  cudaFree(net->lr); cudaFree(net->err);
+  cudaFree(net->stage_in); cudaFree(net->stage_exp); cudaFree(net->cursor);
+  for (float *p : net->outputs) cudaFree(p);
+  delete net;
+  return 0;
+}
+
+int pb_nnet_num_layers(const pb_nnet *net, int32_t *n) {
+  PB_CHECK(net && n, "pb_nnet_num_layers: null");
+  *n = (int32_t)net->layers.size();
+  return 0;
+}
+
+int pb_nnet_total_weights(const pb_nnet *net, int64_t *n) {
+  PB_CHECK(net && n, "pb_nnet_total_weights: null");
+  *n = net->total_w;
+  return 0;
+}
+
+int pb_nnet_set_weights_f64(pb_nnet *net, int32_t layer, const double *host, int64_t n) {
+  PB_CHECK(net, "pb_nnet_set_weights_f64: null");
+  PB_CHECK(layer >= 0 && layer < (int)net->layers.size(), "Too large layer index");
+  PB_CHECK(n == net->nw[layer], "layer size mismatch!");  // nnet.h:742-745
+  return pb_buffer_write_f64(net->ctx, net->weights + net->w_off[layer], host, (size_t)n);
+}
+
+int pb_nnet_get_weights_f64(pb_nnet *net, int32_t layer, double *host, int64_t n) {
+  PB_CHECK(net, "pb_nnet_get_weights_f64: null");
+  PB_CHECK(layer >= 0 && layer < (int)net->layers.size(), "Too large layer index");
+  PB_CHECK(n == net->nw[layer], "layer size mismatch!");
+  return pb_buffer_read_f64(net->ctx, net->weights + net->w_off[layer], host, (size_t)n);
+}
+
+int pb_nnet_layer_weights_device(pb_nnet *net, int32_t layer, float **dptr) {
+  PB_CHECK(net && dptr, "pb_nnet_layer_weights_device: null");
+  PB_CHECK(layer >= 0 && layer < (int)net->layers.size(), "Too large layer index");
+  *dptr = net->weights + net->w_off[layer];
+  return 0;
+}
+
+int pb_nnet_weights_device(pb_nnet *net, float **dptr) {
+  PB_CHECK(net && dptr, "pb_nnet_weights_device: null");
+  *dptr = net->weights;
+  return 0;
+}
+
+int pb_nnet_deltas_device(pb_nnet *net, float **dptr) {
+  PB_CHECK(net && dptr, "pb_nnet_deltas_device: null");
+  *dptr = net->deltas;
+  return 0;
+}
+
+int pb_nnet_init_xavier(pb_nnet *net, uint64_t seed) {
+  PB_CHECK(net, "pb_nnet_init_xavier: null");
+  pb_context *ctx = net->ctx;
+  for (size_t l = 0; l < net->layers.size(); ++l) {
+    if (net->nw[l] == 0) continue;
+    // stats::Normal(0, 1.0 / num_inputs): variance, nnet/layer.cc:86-88
+    const float stddev = (float)std::sqrt(1.0 / (double)net->ni[l]);
+    pb::xavier_kernel<<<pb_ew_grid(ctx, net->nw[l], 256), 256, 0, ctx->stream>>>(
+        net->weights + net->w_off[l], net->nw[l], stddev, seed,
+        (unsigned long long)net->w_off[l]);
+    PB_LAUNCHED(ctx);
+  }
+  return 0;
+}
+
+int pb_nnet_init_constant(pb_nnet *net, double value) {
+  PB_CHECK(net, "pb_nnet_init_constant: null");
+  for (size_t l = 0; l < net->layers.size(); ++l)
+    if (net->nw[l] &&
+        pb_buffer_fill(net->ctx, net->weights + net->w_off[l], (float)value, (size_t)net->nw[l]))
+      return 1;
+  return 0;
+}
+
+int pb_nnet_set_learning_rate(pb_nnet *net, double learning_rate) {
+  PB_CHECK(net, "pb_nnet_set_learning_rate: null");
+  const float v = (float)learning_rate;
+  return pb_buffer_write_f32(net->ctx, net->lr, &v, 1);
+}
+
+int pb_nnet_evaluate(pb_nnet *net, const float *d_in, int64_t batch, float *d_out) {
+  PB_CHECK(net && d_in, "pb_nnet_evaluate: null");
+  PB_CHECK(batch >= 1 && batch <= net->max_batch,
+           "pb_nnet_evaluate: batch exceeds the max_batch the network was created with");
+  if (pb::forward(net, d_in, batch)) return 1;
+  if (d_out)
+    return pb_buffer_copy(net->ctx, d_out, net->outputs.back(), (size_t)(net->no.back() * batch));
+  return 0;
+}
+
+int pb_nnet_layer_output(pb_nnet *net, int32_t layer, float **dptr) {
+  PB_CHECK(net && dptr, "pb_nnet_layer_output: null");
+  PB_CHECK(layer >= 0 && layer < (int)net->layers.size(), "Too large layer index");
+  *dptr = net->outputs[layer];
+  return 0;
+}
+
+int pb_nnet_error(pb_nnet *net, const float *d_out, const float *d_expected, double *error) {
+  PB_CHECK(net && d_out && d_expected && error, "pb_nnet_error: null");
+  const int64_t n = net->no.back();
+  if (pb_error_value(net->ctx, net->loss, n, d_out, d_expected, net->err, 1)) return 1;
+  std::vector<float> comps((size_t)n);
+  if (pb_buffer_read_f32(net->ctx, net->err, comps.data(), (size_t)n)) return 1;
+  double e = 0;  // host-side ascending sum, nnet.h:307-311
+  for (int64_t i = 0; i < n; ++i) e += (double)comps[i];
+  *error = e;
+  return 0;
+}
+
+int pb_nnet_error_gradients(pb_nnet *net, const float *d_out, const float *d_expected,
+                            float *d_gradients, int64_t batch) {
+  PB_CHECK(net, "pb_nnet_error_gradients: null");
+  return pb_error_gradients(net->ctx, net->loss, net->no.back(), d_out, d_expected,
+                            d_gradients, batch);
+}
+
+int pb_nnet_train(pb_nnet *net, const float *d_in, const float *d_expected,
+                  float *d_input_gradients, const float *d_initial_gradients) {
+  PB_CHECK(net && d_in, "pb_nnet_train: null");
+  PB_CHECK(d_expected || d_initial_gradients, "pb_nnet_train: need expected or gradients");
+  return pb::train_step(net, d_in, d_expected, d_input_gradients, d_initial_gradients);
+}
+
+int pb_nnet_train_loop(pb_nnet *net, const float *d_ins, const float *d_expected,
+                       int64_t n_samples) {
+  PB_CHECK(net && d_ins && d_expected, "pb_nnet_train_loop: null");
+  if (n_samples <= 0) return 0;
+  pb_context *ctx = net->ctx;
+  if (!net->train_exec) {
+    // Capture ONE Train() (fetch sample -> forward -> error gradient ->
+    // reverse loop with in-place SGD -> advance cursor) into a CUDA graph.
+    cudaGraph_t graph = nullptr;
+    const uint64_t before = ctx->launches;
+    PB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int nin = (int)net->ni[0], nout = (int)net->no.back();
+    pb::fetch_sample_kernel<<<pb_div_up(nin + nout, 256), 256, 0, ctx->stream>>>(
+        net->cursor, net->stage_in, net->stage_exp, nin, nout);
+    ctx->launches++;
+    int rc = pb::train_step(net, net->stage_in, net->stage_exp, nullptr, nullptr);
+    pb::advance_cursor_kernel<<<1, 1, 0, ctx->stream>>>(net->cursor);
+    ctx->launches++;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    net->graph_launches = ctx->launches - before;
+    ctx->launches = before;  // captured, not yet executed
+    if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+    if (e != cudaSuccess) return pb::fail(std::string("graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&net->train_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return pb::fail(std::string("graph instantiate: ") + cudaGetErrorString(e));
+  }
+  pb_nnet::Cursor cur{d_ins, d_expected, 0};
+  PB_CUDA(cudaMemcpyAsync(net->cursor, &cur, sizeof(cur), cudaMemcpyHostToDevice, ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));  // `cur` is a stack object
+  for (int64_t i = 0; i < n_samples; ++i) {
+    PB_CUDA(cudaGraphLaunch(net->train_exec, ctx->stream));
+    ctx->launches += net->graph_launches;
+  }
+  return 0;
+}
+
+int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_expected,
+                            int64_t batch) {
+  PB_CHECK(net && d_ins && d_expected, "pb_nnet_batch_gradients: null");
+  PB_CHECK(batch >= 1, "pb_nnet_batch_gradients: empty batch");
+  pb_context *ctx = net->ctx;
+  const int64_t nin = net->ni[0], nout = net->no.back();
+  // Batches larger than max_batch run as chunks; every chunk sees the same
+  // (batch-start) weights and accumulates into the delta buffer.
+  for (int64_t b0 = 0; b0 < batch; b0 += net->max_batch) {
+    const int64_t nb = std::min(net->max_batch, batch - b0);
+    const float *in = d_ins + b0 * nin;
+    if (pb::forward(net, in, nb)) return 1;
+    if (pb_error_gradients(ctx, net->loss, nout, net->outputs.back(), d_expected + b0 * nout,
+                           net->grad_a, nb))
+      return 1;
+    float *g = nullptr;
+    if (pb::backward(net, in, nb, net->grad_a, net->grad_b, PB_WEIGHT_DELTAS, b0 == 0, &g))
+      return 1;
+  }
+  return 0;
+}
+
+int pb_nnet_apply_deltas(pb_nnet *net) {
+  PB_CHECK(net, "pb_nnet_apply_deltas: null");
+  return pb_vector_accumulate(net->ctx, net->weights, net->deltas, net->total_w);
+}
+
+int pb_nnet_batch_train(pb_nnet *net, const float *d_ins, const float *d_expected,
+                        int64_t batch) {
+  if (pb_nnet_batch_gradients(net, d_ins, d_expected, batch)) return 1;
+  return pb_nnet_apply_deltas(net);
+}
+
+}  // extern "C"

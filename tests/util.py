@@ -1,0 +1,90 @@
+"""Shared helpers for the parity tests: build the product network and the
+oracle from ONE spec text, seeded inputs, and the tolerance of record."""
+import numpy as np
+
+import plasticity_b200 as pb
+from oracle import pyoracle as po
+
+# north_star: outputs, gradients and weights within |rel| <= 1e-4 (fp32 device
+# arithmetic against the fp64 oracle).  Elements that cancel to ~0 are judged
+# against the tensor's scale: |a-b| <= RTOL*|b| + ATOL_SCALE*max|b|.
+RTOL = 1e-4
+ATOL_SCALE = 1e-5
+
+ACT = {"identity": pb.Identity, "relu": pb.Relu, "leaky": pb.LeakyRelu, "sigmoid": pb.Sigmoid}
+
+
+def architecture_from_spec(text):
+    """spec text (oracle/ref_gen.cc grammar) -> (pb.Architecture, loss)."""
+    model, loss = pb.Architecture(), pb.MeanSquared
+    for raw in text.splitlines():
+        t = raw.split("#")[0].split()
+        if not t:
+            continue
+        k, a = t[0], t[1:]
+        if k == "loss":
+            loss = pb.CrossEntropy if a[0] == "ce" else pb.MeanSquared
+        elif k == "act":
+            model.AddActivationLayer(ACT[a[1]], int(a[0]))
+        elif k == "dense":
+            model._push(pb._lib.LayerDesc(kind=pb._lib.PB_DENSE, in_=int(a[0]), out=int(a[1])),
+                        "dense_layer")
+        elif k == "conv":
+            v = list(map(int, a))
+            model._push(pb._lib.LayerDesc(kind=pb._lib.PB_CONVOLUTION, width=v[0], height=v[1],
+                                          depth=v[2], filter_width=v[3], filter_height=v[4],
+                                          filter_depth=v[5], stride=v[6], padding=v[7],
+                                          num_filters=v[8]), "convolution_layer")
+        elif k == "pool":
+            v = list(map(int, a))
+            model.AddMaxPoolLayer(pb.VolumeDimensions(*v[:3]), pb.AreaDimensions(*v[3:]))
+        elif k == "softmax":
+            model.AddSoftmaxLayer(int(a[0]))
+    return model, loss
+
+
+def f32(a):
+    """Round to fp32 and back: values the device can hold exactly."""
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def xavier_like(net, rng, scale=1.0):
+    """Weights ~ N(0, scale^2/fan_in) per layer so activations stay O(1).
+    `net` is an oracle RestatedNet (it knows each layer's kind)."""
+    w = np.zeros(net.total_w)
+    for l in range(net.n_layers):
+        if not net.nw[l]:
+            continue
+        L = net.layers[l]
+        fan_in = (L.in_ + 1) if L.kind == po.KINDS["dense"] else (L.fw * L.fh * L.fd + 1)
+        w[net.w_off[l]:net.w_off[l + 1]] = rng.normal(0, scale / np.sqrt(fan_in), net.nw[l])
+    return f32(w)
+
+
+def assert_close(actual, expected, what="", rtol=RTOL, atol_scale=ATOL_SCALE):
+    actual = np.asarray(actual, dtype=np.float64)
+    expected = np.asarray(expected, dtype=np.float64)
+    assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
+    scale = float(np.max(np.abs(expected))) if expected.size else 0.0
+    tol = rtol * np.abs(expected) + atol_scale * scale
+    err = np.abs(actual - expected)
+    bad = err > tol
+    if bad.any():
+        i = int(np.argmax(err - tol))
+        raise AssertionError(
+            f"{what}: {int(bad.sum())}/{bad.size} outside |rel|<={rtol} (atol {atol_scale}*max): "
+            f"worst idx {i} got {actual.flat[i]!r} want {expected.flat[i]!r} scale {scale:g}")
+
+
+def load_product_weights(pnet, onet, weights):
+    for l in range(onet.n_layers):
+        if onet.nw[l]:
+            pnet.SetLayerWeights(l, onet.layer_weights(weights, l))
+
+
+def read_product_weights(pnet, onet):
+    w = np.zeros(onet.total_w)
+    for l in range(onet.n_layers):
+        if onet.nw[l]:
+            w[onet.w_off[l]:onet.w_off[l + 1]] = pnet.GetLayerWeights(l)
+    return w
