@@ -66,7 +66,8 @@ def assert_close(actual, expected, what="", rtol=RTOL, atol_scale=ATOL_SCALE):
     expected = np.asarray(expected, dtype=np.float64)
     assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
     scale = float(np.max(np.abs(expected))) if expected.size else 0.0
-    tol = rtol * np.abs(expected) + atol_scale * scale
+    # 1.2e-38: below the fp32 normal range the device flushes toward zero.
+    tol = rtol * np.abs(expected) + atol_scale * scale + 1.2e-38
     err = np.abs(actual - expected)
     bad = err > tol
     if bad.any():
