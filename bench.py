@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py — CIFAR CNN training throughput of the B200 layer path.
+
+Metric (BASELINE.json): CIFAR CNN train samples/sec, beside the reference's
+host-CPU path, with the dominant kernel's fraction of the FP32 roofline.
+
+Workload ("cifar_cnn_batch_train"): the 13-layer network of
+nnet/cifar_test.cc:293-350 (22 466 parameters), cross-entropy, lr 1e-4,
+synthetic images (pixels ~ U{-128..127}, L2-normalised per image like
+cifar_test.cc:66-81, one-hot labels), trained in the gradient-sum minibatch
+mode (Nnet::BatchTrain semantics, W <- W - lr * sum_b grad_b(W_old)) with
+--batch samples per GPU per step: the only training mode of the path that
+shards.  N > 1: one process per GPU, weak scaling, one all-reduce of the
+22 466-float delta buffer per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]
+  python bench.py --impl reference ...     # the reference's CPU path (oracle/_ref)
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cifar_cnn_train_samples_per_sec"
+UNIT = "samples/s"
+# fwd + input-grad + weight-grad MACs of the CIFAR net, x2.
+TRAIN_FLOP_PER_SAMPLE = 23.52e6
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4
+
+
+def cifar_model(pb):
+    m = pb.Architecture(32 * 32 * 3)
+    m.AddConvolutionLayer(pb.VolumeDimensions(32, 32, 3), pb.FilterParams(5, 5, 3, 1, 2, 16))
+    m.AddMaxPoolLayer(pb.VolumeDimensions(32, 32, 16), pb.AreaDimensions(16, 16))
+    m.AddConvolutionLayer(pb.VolumeDimensions(16, 16, 16), pb.FilterParams(5, 5, 16, 1, 2, 20))
+    m.AddMaxPoolLayer(pb.VolumeDimensions(16, 16, 20), pb.AreaDimensions(8, 8))
+    m.AddConvolutionLayer(pb.VolumeDimensions(8, 8, 20), pb.FilterParams(5, 5, 20, 1, 2, 20))
+    m.AddMaxPoolLayer(pb.VolumeDimensions(8, 8, 20), pb.AreaDimensions(4, 4))
+    m.AddDenseLayer(10, pb.Identity)
+    m.AddSoftmaxLayer(10)
+    return m
+
+
+def synthetic_cifar(np, n, seed):
+    rng = np.random.default_rng(seed)
+    px = rng.integers(-128, 128, size=(n, 3072)).astype(np.float64)  # signed char pixels
+    norm = np.sqrt((px * px).sum(axis=1, keepdims=True))
+    norm[norm == 0] = 1.0
+    x = (px / norm).astype(np.float32)
+    lab = rng.integers(0, 10, size=n)
+    e = np.zeros((n, 10), dtype=np.float32)
+    e[np.arange(n), lab] = 1.0
+    return x, e
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 0.2] or self.rows[-3:]
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_rate(np, steps, warmup, sample, threads_note=True):
+    """Time the reference's own CPU implementation of the workload: the
+    kernels emitted by the reference's generator, host-compiled (oracle/_ref),
+    or the plain-C port when that build is absent.  Gradient-sum minibatch,
+    examples spread over all host threads."""
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    from oracle import pyoracle as po
+    if po.RefNet.available("cifar"):
+        net, kind = po.RefNet("cifar"), "reference"
+    else:
+        net, kind = po.RestatedNet(po.spec_text("cifar")), "port"
+    x, e = synthetic_cifar(np, sample, 1234)
+    x, e = x.astype(np.float64), e.astype(np.float64)
+    rng = np.random.default_rng(5)
+    w = np.zeros(net.total_w)
+    for l in range(net.n_layers):  # Xavier: N(0, 1/num_inputs), nnet/layer.cc:86-100
+        if net.nw[l]:
+            w[net.w_off[l]:net.w_off[l + 1]] = rng.normal(0, (1.0 / net.ni[l]) ** 0.5, net.nw[l])
+    for _ in range(warmup):
+        net.batch_train_mt(x, e, w, 1e-4)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        net.batch_train_mt(x, e, w, 1e-4)
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    return {"value": steps * sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{steps} steps x {sample} samples of the same workload "
+                      f"(gradient-sum minibatch, OpenMP over examples, double precision)",
+            "seconds": dt}
+
+
+def run_reference(args):
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = args.ref_sample
+    r = reference_rate(np, args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cifar_cnn_batch_train", "mode": "gradient_sum_minibatch",
+                   "batch_per_step": sample, "lr": 1e-4, "loss": "cross_entropy",
+                   "network": "nnet/cifar_test.cc:293-350 (13 layers, 22466 params)"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def kernel_table(pb, L, np, net, ctx, stream, torch, batch):
+    """Time every (layer, kernel) of one training step in isolation with CUDA
+    events on the library's stream; returns rows sorted by time."""
+    import ctypes as C
+    model = net.model_
+    rows = []
+    lr = C.c_void_p()
+    L.call("pb_buffer_alloc", ctx, 1, C.byref(lr))
+    L.call("pb_buffer_fill", ctx, lr, 1e-4, 1)
+
+    def dev(n, val=None):
+        p = C.c_void_p()
+        L.call("pb_buffer_alloc", ctx, n, C.byref(p))
+        L.call("pb_buffer_fill", ctx, p, 0.01 if val is None else val, n)
+        return p
+
+    def timeit(fn, reps=5):
+        fn()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for i, layer in enumerate(model.layers):
+        d = layer.desc
+        ni, no, nw = layer.num_inputs, layer.num_outputs, layer.weights.size
+        I, O, G, dI = dev(ni * batch), dev(no * batch), dev(no * batch), dev(ni * batch)
+        W = dev(nw) if nw else None
+        out = dev(nw) if nw else None
+        macs = 0
+        if d.kind == L.PB_CONVOLUTION:
+            macs = no * d.filter_width * d.filter_height * d.filter_depth
+        elif d.kind == L.PB_DENSE:
+            macs = ni * no
+        t = timeit(lambda: L.call("pb_layer_evaluate", ctx, C.byref(d), I, W, O, batch))
+        rows.append({"layer": layer.LayerSuffix(), "kernel": "evaluate", "ms": t,
+                     "flop": 2.0 * macs * batch, "bytes": 4.0 * (ni + no) * batch})
+        t = timeit(lambda: L.call("pb_layer_input_delta", ctx, C.byref(d), I, W, G, dI, batch))
+        rows.append({"layer": layer.LayerSuffix(), "kernel": "input_delta", "ms": t,
+                     "flop": 2.0 * macs * batch, "bytes": 4.0 * (ni + no) * batch})
+        if nw:
+            t = timeit(lambda: L.call("pb_layer_weight_update", ctx, C.byref(d), I, W, G, out, lr,
+                                      L.PB_WEIGHT_DELTAS, batch))
+            rows.append({"layer": layer.LayerSuffix(), "kernel": "weight_update", "ms": t,
+                         "flop": 2.0 * macs * batch, "bytes": 4.0 * (ni + no) * batch})
+        for p in (I, O, G, dI, W, out):
+            if p is not None:
+                L.call("pb_buffer_free", ctx, p)
+    L.call("pb_buffer_free", ctx, lr)
+    rows.sort(key=lambda r: -r["ms"])
+    return rows
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import plasticity_b200 as pb
+    from plasticity_b200 import _lib as L
+
+    B = args.batch
+    ctx = pb.nnet.context(local)
+    sp = C.c_void_p()
+    L.call("pb_context_stream", ctx, C.byref(sp))
+    stream = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", local))
+
+    model = cifar_model(pb)
+    net = pb.Nnet(model, pb.Xavier, pb.CrossEntropy, max_batch=B, device=local, seed=42)
+    net.SetLearningParameters(pb.Nnet.LearningParameters(1e-4))
+
+    comm = None
+    if world > 1:
+        idbuf = torch.zeros(L.PB_COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_char * L.PB_COMM_ID_BYTES)()
+            L.call("pb_comm_unique_id", raw)
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = bytes(idbuf.cpu().numpy().tobytes())
+        comm = C.c_void_p()
+        L.call("pb_comm_create", ctx, raw, rank, world, C.byref(comm))
+        # Same starting weights on every rank (replicas): rank 0's Xavier draw.
+        tw = C.c_int64()
+        L.call("pb_nnet_total_weights", net.h, C.byref(tw))
+        wp = C.c_void_p()
+        L.call("pb_nnet_weights_device", net.h, C.byref(wp))
+        if rank != 0:
+            L.call("pb_buffer_fill", ctx, wp, 0.0, tw.value)
+        L.call("pb_comm_allreduce_sum", comm, wp, tw.value)
+
+    # Resident data: NB distinct batches, rotated so consecutive steps never
+    # re-read the same inputs; a step's working set (~54k activations x4 B x B
+    # samples forward + the same backward) is far larger than the 126 MB L2.
+    NB = 8
+    x, e = synthetic_cifar(np, NB * B, 1000 + rank)
+    px, pe = C.c_void_p(), C.c_void_p()
+    L.call("pb_buffer_alloc", ctx, x.size, C.byref(px))
+    L.call("pb_buffer_alloc", ctx, e.size, C.byref(pe))
+    L.call("pb_buffer_write_f32", ctx, px, x.ctypes.data, x.size)
+    L.call("pb_buffer_write_f32", ctx, pe, e.ctypes.data, e.size)
+
+    def step_resident(i):
+        off = (i % NB) * B
+        xi = C.c_void_p(px.value + off * 3072 * 4)
+        ei = C.c_void_p(pe.value + off * 10 * 4)
+        if comm is None:
+            L.call("pb_nnet_batch_train", net.h, xi, ei, B)
+        else:
+            L.call("pb_nnet_batch_train_dp", net.h, comm, xi, ei, B)
+
+    def barrier():
+        L.call("pb_context_finish", ctx)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def launches():
+        n = C.c_uint64()
+        L.call("pb_context_launch_count", ctx, C.byref(n))
+        return n.value
+
+    def maxreduce(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident timing ------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = launches()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = maxreduce(e0.elapsed_time(e1))
+    n_launch = launches() - l0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---------------- end to end through the host API ------------------------
+    # Every step: H2D of that step's inputs + labels from pinned host memory,
+    # BatchTrain, D2H of the step's network outputs (batch x 10 class scores).
+    hx, he, ho = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    L.call("pb_host_alloc", x.nbytes, C.byref(hx))
+    L.call("pb_host_alloc", e.nbytes, C.byref(he))
+    L.call("pb_host_alloc", B * 10 * 4, C.byref(ho))
+    C.memmove(hx, x.ctypes.data, x.nbytes)
+    C.memmove(he, e.ctypes.data, e.nbytes)
+    sx, se = C.c_void_p(), C.c_void_p()
+    L.call("pb_buffer_alloc", ctx, B * 3072, C.byref(sx))
+    L.call("pb_buffer_alloc", ctx, B * 10, C.byref(se))
+    last = C.c_void_p()
+    L.call("pb_nnet_layer_output", net.h, net.number_of_layers() - 1, C.byref(last))
+
+    def step_e2e(i):
+        off = (i % NB) * B
+        L.call("pb_buffer_write_f32_async", ctx, sx, C.c_void_p(hx.value + off * 3072 * 4), B * 3072)
+        L.call("pb_buffer_write_f32_async", ctx, se, C.c_void_p(he.value + off * 10 * 4), B * 10)
+        if comm is None:
+            L.call("pb_nnet_batch_train", net.h, sx, se, B)
+        else:
+            L.call("pb_nnet_batch_train_dp", net.h, comm, sx, se, B)
+        L.call("pb_buffer_read_f32_async", ctx, last, ho, B * 10)
+        L.call("pb_context_finish", ctx)  # the caller holds the result
+
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    e2 = torch.cuda.Event(enable_timing=True)
+    e3 = torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    e3.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e = maxreduce(max(e2.elapsed_time(e3), wall_ms))
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---------------- per-kernel table + roofline (rank 0) ---------------------
+    line = None
+    if rank == 0:
+        tf = C.c_double()
+        L.call("pb_measure_fp32_tflops", ctx, C.byref(tf))
+        rows = kernel_table(pb, L, np, net, ctx, stream, torch, B)
+        step_ms = ms / args.steps
+        total_iso = sum(r["ms"] for r in rows)
+        top = rows[0]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        if top["flop"] > 0:
+            roof = {"bound": "fp32", "kernel": f'{top["layer"]}:{top["kernel"]}',
+                    "achieved": top["flop"] / (top["ms"] * 1e-3) / 1e12, "peak": tf.value,
+                    "unit": "TFLOP/s", "traffic": None,
+                    "peak_source": "FFMA micro-benchmark in this run (pb_measure_fp32_tflops); "
+                                   f"nominal {NOMINAL_FP32_TFLOPS:.1f}; MEASURED_PEAKS.json has "
+                                   "no FP32 entry",
+                    "share_of_step": top["ms"] / total_iso}
+        else:
+            roof = {"bound": "hbm", "kernel": f'{top["layer"]}:{top["kernel"]}',
+                    "achieved": top["bytes"] / (top["ms"] * 1e-3) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                    "share_of_step": top["ms"] / total_iso}
+        roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
+        whole = {"achieved_tflops": TRAIN_FLOP_PER_SAMPLE * B / (step_ms * 1e-3) / 1e12 if world == 1
+                 else TRAIN_FLOP_PER_SAMPLE * B * world / (step_ms * 1e-3) / 1e12,
+                 "fp32_peak_tflops_measured": tf.value * world,
+                 "flop_per_sample": TRAIN_FLOP_PER_SAMPLE}
+        whole["frac"] = whole["achieved_tflops"] / whole["fp32_peak_tflops_measured"]
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = reference_rate(np, 2, 1, args.ref_sample)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cifar_cnn_batch_train", "mode": "gradient_sum_minibatch",
+                       "batch_per_gpu": B, "global_batch": B * world, "lr": 1e-4,
+                       "loss": "cross_entropy",
+                       "network": "nnet/cifar_test.cc:293-350 (13 layers, 22466 params)",
+                       "parallelism": f"dp{world}",
+                       "l2": f"inputs rotate over {NB} resident batches; per-step working set "
+                             f"~{2 * 54366 * 4 * B / 1e6:.0f} MB > 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": (B * 3072 + B * 10) * 4,
+                    "d2h_bytes_per_step": B * 10 * 4},
+            "gpu_launches": n_launch,
+            "roofline": roof,
+            "whole_step": whole,
+            "cpu_baseline": cpu,
+            "top_kernels": [{"k": f'{r["layer"]}:{r["kernel"]}', "ms": round(r["ms"], 4)}
+                            for r in rows[:6]],
+        }
+        if args.table:
+            with open(args.table, "w") as f:
+                json.dump({"batch": B, "step_ms": step_ms, "fp32_peak_tflops": tf.value,
+                           "rows": rows}, f, indent=1)
+    barrier()
+    if comm is not None:
+        L.call("pb_comm_destroy", comm)
+    if world > 1:
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="samples per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-sample", type=int, default=256,
+                    help="samples per step of the CPU arm (bounded sample of the workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table", default=None, help="write the per-kernel table (JSON) here")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

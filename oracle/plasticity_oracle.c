@@ -540,6 +540,40 @@ void po_net_batch_train(const po_layer *layers, int n_layers, int loss,
   free(frozen); free(delta); free(lo); free(grad);
 }
 
+/* po_net_batch_train with examples spread over host threads (see
+ * oracle/ref_driver.cc: ref_net_batch_train_mt). CPU-baseline timing only. */
+void po_net_batch_train_mt(const po_layer *layers, int n_layers, int loss,
+                           const double *ins, const double *expected, long batch,
+                           double *weights, double lr) {
+  const long nin = po_num_inputs(&layers[0]);
+  const long nout = po_num_outputs(&layers[n_layers - 1]);
+  const long tw = po_net_total_weights(layers, n_layers);
+  const long to = po_net_total_outputs(layers, n_layers);
+  const long max_io = net_max_io(layers, n_layers);
+  double *frozen = (double *)malloc(sizeof(double) * (size_t)tw);
+  double *total = (double *)calloc((size_t)tw, sizeof(double));
+  memcpy(frozen, weights, sizeof(double) * (size_t)tw);
+#pragma omp parallel
+  {
+    double *delta = (double *)calloc((size_t)tw, sizeof(double));
+    double *sum = (double *)calloc((size_t)tw, sizeof(double));
+    double *lo = (double *)malloc(sizeof(double) * (size_t)to);
+    double *grad = (double *)malloc(sizeof(double) * (size_t)max_io);
+#pragma omp for schedule(dynamic, 1)
+    for (long b = 0; b < batch; ++b) {
+      po_net_evaluate(layers, n_layers, ins + b * nin, frozen, lo);
+      po_error_gradients(loss, nout, lo + (to - nout), expected + b * nout, grad);
+      net_backward(layers, n_layers, ins + b * nin, frozen, lo, grad, lr, 1, delta);
+      for (long i = 0; i < tw; ++i) sum[i] += delta[i];
+    }
+#pragma omp critical
+    for (long i = 0; i < tw; ++i) total[i] += sum[i];
+    free(delta); free(sum); free(lo); free(grad);
+  }
+  for (long i = 0; i < tw; ++i) weights[i] += total[i];
+  free(frozen); free(total);
+}
+
 void po_net_evaluate_batch(const po_layer *layers, int n_layers,
                            const double *ins, long batch, const double *weights,
                            double *outs) {

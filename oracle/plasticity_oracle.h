@@ -70,6 +70,9 @@ void po_net_train_loop(const po_layer *layers, int n_layers, int loss,
 void po_net_batch_train(const po_layer *layers, int n_layers, int loss,
                         const double *ins, const double *expected, long batch,
                         double *weights, double lr, double *sum_deltas);
+void po_net_batch_train_mt(const po_layer *layers, int n_layers, int loss,
+                           const double *ins, const double *expected, long batch,
+                           double *weights, double lr);
 /* Batched forward of `batch` independent samples (batched inference). */
 void po_net_evaluate_batch(const po_layer *layers, int n_layers,
                            const double *ins, long batch, const double *weights,

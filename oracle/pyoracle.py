@@ -137,6 +137,8 @@ class RestatedNet(_NetBase):
                                             _dp, C.c_double]
             L.po_net_batch_train.argtypes = [lp, C.c_int, C.c_int, _dp, _dp, C.c_long,
                                              _dp, C.c_double, _dp]
+            L.po_net_batch_train_mt.argtypes = [lp, C.c_int, C.c_int, _dp, _dp, C.c_long,
+                                                _dp, C.c_double]
             L.po_net_evaluate_batch.argtypes = [lp, C.c_int, _dp, C.c_long, _dp, _dp]
             L.po_set_threads.argtypes = [C.c_int]
             cls._lib = L
@@ -208,6 +210,10 @@ class RestatedNet(_NetBase):
                                       _p(expected), xs.shape[0], _p(weights), lr, _p(sd))
         return sd
 
+    def batch_train_mt(self, xs, expected, weights, lr):
+        self.lib().po_net_batch_train_mt(self.layers, self.n_layers, self.loss, _p(xs),
+                                         _p(expected), xs.shape[0], _p(weights), lr)
+
     def evaluate_batch(self, xs, weights):
         outs = np.empty((xs.shape[0], self.n_out))
         self.lib().po_net_evaluate_batch(self.layers, self.n_layers, _p(xs),
@@ -252,6 +258,7 @@ class RefNet(_NetBase):
         L.ref_net_train.argtypes = [_dp, _dp, _dp, C.c_double, _dp, _dp, _dp, C.c_int]
         L.ref_net_train_loop.argtypes = [_dp, _dp, C.c_long, _dp, C.c_double, C.c_int]
         L.ref_net_batch_train.argtypes = [_dp, _dp, C.c_long, _dp, C.c_double, _dp]
+        L.ref_net_batch_train_mt.argtypes = [_dp, _dp, C.c_long, _dp, C.c_double]
 
     def set_parallel_threshold(self, n: int):
         C.c_int.in_dll(self.L, "ref_parallel_threshold").value = n
@@ -305,6 +312,10 @@ class RefNet(_NetBase):
         sd = np.empty(self.total_w)
         self.L.ref_net_batch_train(_p(xs), _p(expected), xs.shape[0], _p(weights), lr, _p(sd))
         return sd
+
+
+    def batch_train_mt(self, xs, expected, weights, lr):
+        self.L.ref_net_batch_train_mt(_p(xs), _p(expected), xs.shape[0], _p(weights), lr)
 
 
 def spec_text(name: str) -> str:

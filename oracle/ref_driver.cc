@@ -184,4 +184,37 @@ void ref_net_batch_train(const double *ins, const double *expected, long batch,
   }
 }
 
+
+// Same semantics as ref_net_batch_train with the examples spread over host
+// threads — the reference's BatchTrain gives every example its own command
+// queue (nnet.h:639-648), so examples are the natural unit of host
+// parallelism.  Work-items inside a kernel then run serially on the calling
+// thread (nested OpenMP regions are inactive).  Per-thread delta sums are
+// combined at the end, so the summation order differs from example order by
+// rounding only.  Used for CPU-baseline timing.
+void ref_net_batch_train_mt(const double *ins, const double *expected, long batch,
+                            double *weights, double lr) {
+  const Shape &s = shape();
+  const long nin = s.ni[0], nout = s.no[s.layers - 1];
+  std::vector<double> frozen(weights, weights + s.total_w);
+  std::vector<double> total(s.total_w, 0.0);
+#pragma omp parallel
+  {
+    std::vector<double> layer_out(s.total_o), grad(s.max_io), delta(s.total_w, 0.0),
+        sum(s.total_w, 0.0);
+#pragma omp for schedule(dynamic, 1)
+    for (long b = 0; b < batch; ++b) {
+      Forward(ins + b * nin, frozen.data(), layer_out.data());
+      ref_error_gradients(layer_out.data() + s.o_off[s.layers - 1],
+                          const_cast<double *>(expected + b * nout), grad.data());
+      Backward(ins + b * nin, frozen.data(), layer_out.data(), grad.data(), lr, 1,
+               delta.data());
+      for (long i = 0; i < s.total_w; ++i) sum[i] += delta[i];
+    }
+#pragma omp critical
+    for (long i = 0; i < s.total_w; ++i) total[i] += sum[i];
+  }
+  for (long i = 0; i < s.total_w; ++i) weights[i] += total[i];
+}
+
 }  // extern "C"
