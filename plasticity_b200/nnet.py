@@ -186,7 +186,7 @@ class Architecture:
         return self.layers[-1].num_outputs
 
     def to_spec(self, loss: int) -> str:
-        """Spec text understood by oracle/ (tests build the oracle from it)."""
+        """One line per layer in the plain-text layer grammar the tests use."""
         head = "loss ce" if loss == CrossEntropy else "loss mse"
         return "\n".join([head] + [l.spec_line() for l in self.layers]) + "\n"
 

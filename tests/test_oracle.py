@@ -1,0 +1,329 @@
+"""CPU tests (no GPU): pin the oracle.
+
+1. The plain-C restatement (oracle/plasticity_oracle.c) is BIT-IDENTICAL to the
+   reference's own generated kernels compiled for the host (oracle/_ref) on
+   every spec — run where oracle/_ref exists (the build container; the .so
+   files also travel to the GPU box).
+2. Both reproduce the known answers of the reference's nnet/nnet_test.cc.
+3. The restatement reproduces the committed golden fixtures (generated from
+   oracle/_ref by tests/golden/make_golden.py).
+"""
+import glob
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SPECS = sorted(os.path.basename(p)[:-5] for p in
+               glob.glob(os.path.join(os.path.dirname(po.__file__), "specs", "*.spec")))
+GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")))
+REF_UNDEFINED = {"savefmt"}  # reference reads GRADIENT out of bounds (2x2 / pad 0 conv)
+
+
+def nets(name):
+    out = [po.RestatedNet(po.spec_text(name))]
+    if po.RefNet.available(name):
+        out.append(po.RefNet(name))
+    return out
+
+
+def dense_w(n_in, rows):
+    """rows: [(w0, w1, ..., bias)] per node -> flat reference layout."""
+    return np.array([v for r in rows for v in r], dtype=np.float64)
+
+
+@pytest.mark.parametrize("name", SPECS)
+def test_restatement_is_bit_identical_to_reference_kernels(name):
+    if not po.RefNet.available(name):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    R, S = po.RefNet(name), po.RestatedNet(po.spec_text(name))
+    assert (R.ni, R.no, R.nw) == (S.ni, S.no, S.nw)
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    w = util.xavier_like(S, rng)
+    for trial in range(3):
+        x = rng.normal(0, 1, R.n_in)
+        e = rng.uniform(0, 1, R.n_out)
+        assert np.array_equal(R.evaluate(x, w), S.evaluate(x, w))
+        out = S.layer_output(S.evaluate(x, w), S.n_layers - 1).copy()
+        assert R.error(out, e) == S.error(out, e)
+        assert np.array_equal(R.error_gradients(out, e), S.error_gradients(out, e))
+        for l in range(S.n_layers):
+            I = rng.normal(0, 1, S.ni[l])
+            G = rng.normal(0, 1, S.no[l])
+            W = S.layer_weights(w, l).copy()
+            assert np.array_equal(R.evaluate_layer(l, I, W), S.evaluate_layer(l, I, W)), l
+            if name not in REF_UNDEFINED:
+                assert np.array_equal(R.input_delta(l, I, W, G), S.input_delta(l, I, W, G)), l
+            if S.nw[l]:
+                for mode in (0, 1):
+                    assert np.array_equal(R.weight_update(l, I, W, G, 0.3, mode),
+                                          S.weight_update(l, I, W, G, 0.3, mode)), (l, mode)
+        if name in REF_UNDEFINED:
+            continue
+        w1, w2 = w.copy(), w.copy()
+        _, g1 = R.train(x, e, w1, 0.01, True)
+        _, g2 = S.train(x, e, w2, 0.01, True)
+        assert np.array_equal(w1, w2) and np.array_equal(g1, g2)
+        xs = rng.normal(0, 1, (3, R.n_in))
+        es = rng.uniform(0, 1, (3, R.n_out))
+        w1, w2 = w.copy(), w.copy()
+        d1 = R.batch_train(xs, es, w1, 0.01)
+        d2 = S.batch_train(xs, es, w2, 0.01)
+        assert np.array_equal(w1, w2) and np.array_equal(d1, d2)
+        w = w1
+
+
+def test_double_forward_of_train_changes_nothing():
+    """Nnet::Train runs Evaluate twice (nnet.h:384 and :477); results equal."""
+    if not po.RefNet.available("mixed"):
+        pytest.skip("oracle/_ref not built")
+    R = po.RefNet("mixed")
+    S = po.RestatedNet(po.spec_text("mixed"))
+    rng = np.random.default_rng(3)
+    w = util.xavier_like(S, rng)
+    x, e = rng.normal(0, 1, R.n_in), rng.uniform(0, 1, R.n_out)
+    w1, w2 = w.copy(), w.copy()
+    R.train(x, e, w1, 0.1, forwards=1)
+    R.train(x, e, w2, 0.1, forwards=2)
+    assert np.array_equal(w1, w2)
+
+
+# ---- known answers of nnet/nnet_test.cc -----------------------------------------
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_one_layer_relu_known_answer(which):
+    """nnet_test.cc:17-70: dense 3->3 + ReLU, {.1,.2,.7} -> {1.35,1.27,1.8}."""
+    ns = nets("relu3")
+    if which >= len(ns):
+        pytest.skip("oracle/_ref not built")
+    n = ns[which]
+    w = dense_w(3, [(0.1, 0.3, 0.4, 1), (0.2, 0.2, 0.3, 1), (0.3, 0.7, 0.9, 1)])
+    out = n.layer_output(n.evaluate(np.array([0.1, 0.2, 0.7]), w), n.n_layers - 1)
+    assert out == pytest.approx([1.35, 1.27, 1.8], rel=1e-3)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_simple_network_known_answer(which):
+    """nnet_test.cc:74-190: 3-3-3-3 ReLU/Sigmoid/Identity + softmax; CE loss."""
+    ns = nets("simple3")
+    if which >= len(ns):
+        pytest.skip("oracle/_ref not built")
+    n = ns[which]
+    w = np.concatenate([
+        dense_w(3, [(0.1, 0.3, 0.4, 1), (0.2, 0.2, 0.3, 1), (0.3, 0.7, 0.9, 1)]),
+        dense_w(3, [(0.2, 0.3, 0.6, 1), (0.3, 0.5, 0.4, 1), (0.5, 0.7, 0.8, 1)]),
+        dense_w(3, [(0.1, 0.3, 0.5, 1), (0.4, 0.7, 0.2, 1), (0.8, 0.2, 0.9, 1)])])
+    out = n.layer_output(n.evaluate(np.array([0.1, 0.2, 0.7]), w), n.n_layers - 1)
+    assert out == pytest.approx([0.19858, 0.28559, 0.51583], rel=1e-3)
+    err = n.error(np.array([0.26980, 0.32235, 0.40784]), np.array([1.0, 0.0, 0.0]))
+    assert err == pytest.approx(1.310074, rel=1.2e-5)  # Catch Approx default
+
+
+MAZUR_W = np.concatenate([dense_w(2, [(0.15, 0.2, 0.35), (0.25, 0.3, 0.35)]),
+                          dense_w(2, [(0.4, 0.45, 0.6), (0.5, 0.55, 0.6)])])
+MAZUR_EXPECT = {  # nnet_test.cc:260-273 — (layer block, node, edge): weight after one step
+    (0, 0, 0): 0.149780716, (0, 0, 1): 0.19956143, (0, 1, 0): 0.24975114, (0, 1, 1): 0.29950229,
+    (1, 0, 0): 0.35891648, (1, 0, 1): 0.408666186, (1, 1, 0): 0.511301270, (1, 1, 1): 0.561370121}
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_mattmazur_forward_loss_and_sgd_step(which):
+    """nnet_test.cc:194-274.  The reference's own constants (0.75136507 ...)
+    assume e; the generated kernels use 2.71828, a 2e-7 relative shift that
+    Catch's Approx (1.2e-5) absorbs."""
+    ns = nets("mazur")
+    if which >= len(ns):
+        pytest.skip("oracle/_ref not built")
+    n = ns[which]
+    x, e = np.array([0.05, 0.10]), np.array([0.01, 0.99])
+    out = n.layer_output(n.evaluate(x, MAZUR_W), n.n_layers - 1)
+    assert out == pytest.approx([0.75136507, 0.772928465], rel=1.2e-5)
+    assert n.error(np.array([0.75136507, 0.772928465]), e) == pytest.approx(0.298371109, rel=1.2e-5)
+    w = MAZUR_W.copy()
+    n.train(x, e, w, 0.5)
+    for (blk, node, edge), want in MAZUR_EXPECT.items():
+        assert w[blk * 6 + node * 3 + edge] == pytest.approx(want, rel=1.2e-5)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_mattmazur_split_network_backprop(which):
+    """nnet_test.cc:276-348: two Nnets chained through input_gradients /
+    custom initial gradients give the same 8 weights."""
+    ns = nets("mazur_half")
+    if which >= len(ns):
+        pytest.skip("oracle/_ref not built")
+    n = ns[which]
+    wa, wb = MAZUR_W[:6].copy(), MAZUR_W[6:].copy()
+    x, e = np.array([0.05, 0.10]), np.array([0.01, 0.99])
+    mid = n.layer_output(n.evaluate(x, wa), n.n_layers - 1).copy()
+    _, ig = n.train(mid, e, wb, 0.5, want_input_grads=True)
+    n.train(x, mid, wa, 0.5, initial_gradients=ig)
+    w = np.concatenate([wa, wb])
+    for (blk, node, edge), want in MAZUR_EXPECT.items():
+        assert w[blk * 6 + node * 3 + edge] == pytest.approx(want, rel=1.2e-5)
+
+
+POOL_IN = np.array([1, 0, 0, 3, 32, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 5,
+                    1, 0, 0, 3, 7, 8, 10, 2, 0, 0, 5, 0, 1, 0, 0, 5,
+                    1, -8, 0, 3, 32, 24, 0, 2, 0, 100, 0, 0, 0, 0, 0, 5], dtype=np.float64)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_max_pool_known_answer(which):
+    """nnet_test.cc:351-484: forward maxima; backward exact zeros off the maxima,
+    every TIED maximum (the all-zero window at 8,9,12,13) receives the gradient."""
+    ns = nets("maxpool443")
+    if which >= len(ns):
+        pytest.skip("oracle/_ref not built")
+    n = ns[which]
+    w = np.zeros(0)
+    out = n.layer_output(n.evaluate(POOL_IN, w), n.n_layers - 1)
+    assert np.array_equal(out, [32, 3, 0, 5, 8, 10, 1, 5, 32, 3, 100, 5])
+    altered = np.array([33, 3, 100, 4, 8, 10, 1, 5, 31, 4, 90, 6], dtype=np.float64)
+    _, g = n.train(POOL_IN, altered, w, 1.0, want_input_grads=True)
+    neg = {4, 8, 9, 12, 13, 35, 47}
+    pos = {15, 36, 41}
+    for i in range(48):
+        if i in neg:
+            assert g[i] < 0, i
+        elif i in pos:
+            assert g[i] > 0, i
+        else:
+            assert g[i] == 0.0, i
+
+
+def conv553_weights():
+    """cs231n demo filters, nnet_test.cc:608-694, in [f][z][row][col]+bias layout."""
+    f0 = [[[0, 1, 0], [0, -1, 1], [-1, 1, 0]],
+          [[0, -1, 1], [0, -1, -1], [0, 0, -1]],
+          [[-1, -1, 1], [1, 1, 0], [0, 1, 1]]]
+    f1 = [[[0, -1, -1], [1, 1, 0], [0, 0, 0]],
+          [[0, -1, -1], [0, 0, 0], [1, 0, -1]],
+          [[1, 1, -1], [1, 1, 0], [1, 0, 0]]]
+    return np.concatenate([np.array(f0, dtype=np.float64).reshape(-1), [1.0],
+                           np.array(f1, dtype=np.float64).reshape(-1), [0.0]])
+
+
+CONV_IN = np.array([1, 0, 0, 1, 1, 2, 0, 0, 2, 1, 0, 1, 1, 2, 0, 1, 0, 0, 2, 1, 2, 2, 1, 1, 1,
+                    0, 2, 0, 0, 1, 1, 1, 1, 1, 2, 1, 1, 0, 1, 1, 1, 1, 1, 0, 2, 2, 0, 2, 0, 0,
+                    2, 0, 2, 1, 2, 0, 2, 1, 0, 0, 2, 1, 1, 0, 0, 1, 1, 0, 0, 0, 2, 1, 1, 1, 2],
+                   dtype=np.float64)
+CONV_OUT = np.array([3, 4, 1, 8, 0, -2, 2, -1, 2, 2, 4, 6, -5, 5, -1, 1, 3, 2], dtype=np.float64)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_convolution_known_answer(which):
+    """nnet_test.cc:585-775: 18 integer outputs; after perturbing one target the
+    input-gradient support is exactly {0,1,5,25,26,31,50,55,56}."""
+    ns = nets("conv553")
+    if which >= len(ns):
+        pytest.skip("oracle/_ref not built")
+    n = ns[which]
+    w = conv553_weights()
+    assert w.size == 56
+    out = n.layer_output(n.evaluate(CONV_IN, w), n.n_layers - 1)
+    assert np.array_equal(out, CONV_OUT)
+    altered = CONV_OUT.copy()
+    altered[0] = 4
+    _, g = n.train(CONV_IN, altered, w.copy(), 1.0, want_input_grads=True)
+    assert set(np.nonzero(g)[0].tolist()) == {0, 1, 5, 25, 26, 31, 50, 55, 56}
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_softmax_known_answer(which):
+    """nnet_test.cc:995-1016."""
+    ns = nets("softmax3")
+    if which >= len(ns):
+        pytest.skip("oracle/_ref not built")
+    n = ns[which]
+    out = n.layer_output(n.evaluate(np.array([-2.85, 0.86, 0.28]), np.zeros(0)), n.n_layers - 1)
+    assert out == pytest.approx([0.0154493515, 0.631, 0.3533874062], rel=1e-3)
+
+
+def fd_input_gradient(n, x, e, w, eps=1e-6):
+    g = np.zeros_like(x)
+    last = n.n_layers - 1
+    for i in range(x.size):
+        xp, xm = x.copy(), x.copy()
+        xp[i] += eps
+        xm[i] -= eps
+        ep = n.error(n.layer_output(n.evaluate(xp, w), last).copy(), e)
+        em = n.error(n.layer_output(n.evaluate(xm, w), last).copy(), e)
+        g[i] = (ep - em) / (2 * eps)
+    return g
+
+
+@pytest.mark.parametrize("name", ["dense5", "conv331", "softmax3", "mixed", "savefmt"])
+def test_gradients_match_finite_differences(name):
+    """The reference's own gradient-check strategy (nnet_test.cc:777-1053), in
+    double: analytic input gradients vs central differences.  `savefmt` covers
+    the 2x2 / pad-0 convolution where the reference itself reads out of bounds:
+    the restatement's bounds-guarded form is the true gradient there."""
+    n = po.RestatedNet(po.spec_text(name))
+    rng = np.random.default_rng(11)
+    w = util.xavier_like(n, rng)
+    x = rng.normal(0, 1, n.n_in)
+    e = np.full(n.n_out, 0.2)
+    _, g = n.train(x, e, w.copy(), 0.0, want_input_grads=True)
+    fd = fd_input_gradient(n, x, e, w)
+    assert g == pytest.approx(fd, rel=2e-4, abs=1e-7)
+
+
+def test_weight_gradients_match_finite_differences():
+    """nnet_test.cc:828-881, 937-992: weight gradient via one lr=1 step."""
+    for name in ("dense5", "conv331", "mixed"):
+        n = po.RestatedNet(po.spec_text(name))
+        rng = np.random.default_rng(5)
+        w = util.xavier_like(n, rng)
+        x = rng.normal(0, 1, n.n_in)
+        e = np.full(n.n_out, 0.2)
+        w1 = w.copy()
+        n.train(x, e, w1, 1.0)
+        analytic = w - w1
+        last = n.n_layers - 1
+        idx = rng.choice(w.size, size=min(40, w.size), replace=False)
+        for i in idx:
+            wp, wm = w.copy(), w.copy()
+            wp[i] += 1e-6
+            wm[i] -= 1e-6
+            fd = (n.error(n.layer_output(n.evaluate(x, wp), last).copy(), e) -
+                  n.error(n.layer_output(n.evaluate(x, wm), last).copy(), e)) / 2e-6
+            assert analytic[i] == pytest.approx(fd, rel=1e-3, abs=1e-7), (name, i)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_restatement_reproduces_golden_fixtures(name):
+    """tests/golden/*.npz were produced by the reference's generated kernels."""
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    n = po.RestatedNet(po.spec_text(name))
+    w0, xs, es, lr = g["w0"], g["xs"], g["es"], float(g["lr"])
+    lo = n.evaluate(xs[0].copy(), w0.copy())
+    assert np.array_equal(lo, g["layer_out"])
+    assert n.error(n.layer_output(lo, n.n_layers - 1).copy(), es[0].copy()) == float(g["error"])
+    w = w0.copy()
+    for b in range(xs.shape[0]):
+        _, ig = n.train(xs[b].copy(), es[b].copy(), w, lr, want_input_grads=True)
+        assert np.array_equal(ig, g["input_grads"][b])
+        if b == 0:
+            assert np.array_equal(w, g["w_after_1"])
+    assert np.array_equal(w, g["w_after_B"])
+    wb = w0.copy()
+    n.batch_train(xs.copy(), es.copy(), wb, lr)
+    assert np.array_equal(wb, g["w_after_batch"])
+
+
+def test_multithreaded_batch_train_matches_serial():
+    n = po.RestatedNet(po.spec_text("mixed"))
+    rng = np.random.default_rng(2)
+    w = util.xavier_like(n, rng)
+    xs, es = rng.normal(0, 1, (9, n.n_in)), rng.uniform(0, 1, (9, n.n_out))
+    w1, w2 = w.copy(), w.copy()
+    n.batch_train(xs, es, w1, 0.05)
+    n.batch_train_mt(xs, es, w2, 0.05)
+    assert w2 == pytest.approx(w1, rel=1e-12, abs=1e-15)
