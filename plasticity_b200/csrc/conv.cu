@@ -150,6 +150,8 @@ conv_wgrad_general_kernel(const float *__restrict__ I, const float *Wt,
   }
 }
 
+constexpr int64_t kTiledMinBatch = 32;
+
 int conv_check(const pb_layer_desc *l) {
   PB_CHECK(l->filter_depth == l->depth,
            "Convolution layer input depth != filter depth");  // convolution_layer.cc:12-16
@@ -198,12 +200,22 @@ int conv_weight_update_general(pb_context *ctx, const pb_layer_desc *l, const fl
 int conv_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
                   float *O, int64_t batch) {
   if (conv_check(l)) return 1;
+  // Small batches (per-sample SGD) are latency-bound: the one-thread-per-
+  // output kernel spreads a single sample over many more CTAs.
+  if (batch >= kTiledMinBatch) {
+    const int rc = conv_evaluate_tiled(ctx, l, I, W, O, batch);
+    if (rc >= 0) return rc;
+  }
   return conv_evaluate_general(ctx, l, I, W, O, batch);
 }
 
 int conv_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *W, const float *G,
                      float *dI, int64_t batch) {
   if (conv_check(l)) return 1;
+  if (batch >= kTiledMinBatch) {
+    const int rc = conv_input_delta_tiled(ctx, l, W, G, dI, batch);
+    if (rc >= 0) return rc;
+  }
   return conv_input_delta_general(ctx, l, W, G, dI, batch);
 }
 
@@ -211,6 +223,10 @@ int conv_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
                        const float *W, const float *G, float *out, const float *lr,
                        int mode, int64_t batch) {
   if (conv_check(l)) return 1;
+  if (batch >= kTiledMinBatch) {
+    const int rc = conv_weight_update_tiled(ctx, l, I, W, G, out, lr, mode, batch);
+    if (rc >= 0) return rc;
+  }
   return conv_weight_update_general(ctx, l, I, W, G, out, lr, mode, batch);
 }
 

@@ -36,6 +36,16 @@ int conv_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
                        const float *W, const float *G, float *out, const float *lr,
                        int mode, int64_t batch);
 
+// conv_tiled.cu: register-tiled stride-1 kernels; return -1 when the shape is
+// outside their envelope (the caller then uses the general kernels).
+int conv_evaluate_tiled(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
+                        float *O, int64_t batch);
+int conv_input_delta_tiled(pb_context *ctx, const pb_layer_desc *l, const float *W,
+                           const float *G, float *dI, int64_t batch);
+int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                             const float *W, const float *G, float *out, const float *lr,
+                             int mode, int64_t batch);
+
 // Output extent of a convolution, nnet/convolution_layer.cc:36-44.
 static inline int64_t conv_out_w(const pb_layer_desc *l) {
   return (l->width - l->filter_width + 2 * l->padding) / l->stride + 1;

@@ -68,7 +68,7 @@ def ctx():
 
 
 @pytest.mark.parametrize("name", SPECS)
-@pytest.mark.parametrize("batch", [1, 5])
+@pytest.mark.parametrize("batch", [1, 5, 37])
 def test_layer_kernels(ctx, name, batch):
     """evaluate / input_delta / weight kernels of every layer of every spec."""
     spec = po.spec_text(name)
