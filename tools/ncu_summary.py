@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Turn one gpurun round's ncu outputs into the tracked summaries under profiles/.
+
+  python tools/ncu_summary.py <tag>
+
+Reads gpurun_out/launches_<tag>.csv (ncu --metrics gpu__time_duration.sum launch
+list), gpurun_out/prof_<tag>.ncu-rep (ncu --set full capture), bench_<tag>.json and
+table_<tag>.json; writes profiles/<tag>_launches_by_kernel.csv, profiles/<tag>_launches.csv
+(the raw launch list), profiles/<tag>_ncu_full.csv (selected counters per captured launch)
+and copies the bench line / kernel table.
+"""
+import collections
+import csv
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+WANT = [
+    "Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+    "smsp__inst_executed.sum",
+]
+
+
+def main():
+    tag = sys.argv[1]
+    os.makedirs(P, exist_ok=True)
+    lp = os.path.join(G, f"launches_{tag}.csv")
+    if os.path.exists(lp):
+        lines = [l for l in open(lp) if l.startswith('"')]
+        with open(os.path.join(P, f"{tag}_launches.csv"), "w") as f:
+            f.writelines(lines)
+        agg = collections.OrderedDict()
+        for row in csv.DictReader(lines):
+            v = float(row["Metric Value"].replace(",", ""))
+            v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(row["Metric Unit"], 1.0)
+            a = agg.setdefault(row["Kernel Name"], [0, 0.0, row["Grid Size"], row["Block Size"]])
+            a[0] += 1
+            a[1] += v
+        tot = sum(a[1] for a in agg.values())
+        with open(os.path.join(P, f"{tag}_launches_by_kernel.csv"), "w") as f:
+            w = csv.writer(f)
+            w.writerow(["kernel", "launches", "total_us", "avg_us", "share_pct", "grid(last)", "block(last)"])
+            for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                w.writerow([k, a[0], f"{a[1] / 1e3:.1f}", f"{a[1] / a[0] / 1e3:.2f}",
+                            f"{100 * a[1] / tot:.2f}", a[2], a[3]])
+    rp = os.path.join(G, f"prof_{tag}.ncu-rep")
+    if os.path.exists(rp):
+        raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        idx = {h: i for i, h in enumerate(hdr)}
+        cols = [c for c in WANT if c in idx]
+        with open(os.path.join(P, f"{tag}_ncu_full.csv"), "w") as f:
+            w = csv.writer(f)
+            w.writerow([f"{c} [{units[idx[c]]}]" if units[idx[c]] else c for c in cols])
+            for d in data:
+                w.writerow([d[idx[c]] for c in cols])
+    for name in (f"bench_{tag}.json", f"table_{tag}.json"):
+        src = os.path.join(G, name)
+        if os.path.exists(src):
+            shutil.copy(src, os.path.join(P, f"{tag}_{name.split('_')[0]}.json"))
+
+
+if __name__ == "__main__":
+    main()
