@@ -203,7 +203,9 @@ int conv_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, const
   // Small batches (per-sample SGD) are latency-bound: the one-thread-per-
   // output kernel spreads a single sample over many more CTAs.
   if (batch >= kTiledMinBatch) {
-    const int rc = conv_evaluate_tiled(ctx, l, I, W, O, batch);
+    int rc = conv_evaluate_umma(ctx, l, I, W, O, batch);
+    if (rc >= 0) return rc;
+    rc = conv_evaluate_tiled(ctx, l, I, W, O, batch);
     if (rc >= 0) return rc;
   }
   return conv_evaluate_general(ctx, l, I, W, O, batch);
@@ -213,7 +215,9 @@ int conv_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *W, co
                      float *dI, int64_t batch) {
   if (conv_check(l)) return 1;
   if (batch >= kTiledMinBatch) {
-    const int rc = conv_input_delta_tiled(ctx, l, W, G, dI, batch);
+    int rc = conv_input_delta_umma(ctx, l, W, G, dI, batch);
+    if (rc >= 0) return rc;
+    rc = conv_input_delta_tiled(ctx, l, W, G, dI, batch);
     if (rc >= 0) return rc;
   }
   return conv_input_delta_general(ctx, l, W, G, dI, batch);

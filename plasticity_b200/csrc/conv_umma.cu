@@ -1,0 +1,404 @@
+// 3xTF32 tcgen05 implicit-GEMM convolution (forward and input-gradient) for the
+// batched stride-1 "same" convolutions of the CIFAR network
+// (nnet/cifar_test.cc:293-350; semantics nnet/convolution_layer.cc:50-224).
+//
+//   Out[b,oc,r,c] = bias_oc + sum_{ic,fy,fx} Wk[oc,ic,fy,fx] * In0[b,ic,r-p+fy,c-p+fx]
+//
+// (input-gradient: In = G, Wk = flipped / channel-transposed filters, no bias;
+// with pad == filter/2 the reference's centre guard, convolution_layer.cc:209,
+// is the identity.)
+//
+// GEMM view: M = output pixels, N = output channels, K = (tap, input channel).
+// The image of one work item (a sample, or a 16-row block of it) is stored
+// ONCE in shared memory as [4-channel chunk][padded pixel][4 floats], split
+// into a TF32 "hi" plane set and an fp32-residual "lo" plane set.  That layout
+// is exactly tcgen05's K-major no-swizzle canonical operand layout
+//   byte(row m, chunk) = chunk*LBO + (m/8)*SBO + (m%8)*16
+// with SBO = padded image-row pitch: an M-tile is an 8-pixel-wide strip of 16
+// (or 8) image rows, and moving the descriptor's start address by
+// (fy*pitch + fx)*16 bytes selects filter tap (fy,fx) — no im2col copy exists
+// anywhere.  One K=8 MMA covers two 4-channel chunks (LBO = their distance).
+// (Layout rules validated on B200 by tools/umma_probe.cu.)
+//
+// 3xTF32: x = hi + lo, hi = tf32(x).  Per K block two MMAs:
+//   D[:, 0:N1]  += A_hi * [B_hi | B_lo]      (hi*hi and hi*lo side by side in N)
+//   D[:, 0:N2]  += A_lo * B_hi               (accumulated onto the hi*hi columns)
+// and the epilogue adds the two column groups: fp32-level accuracy (dropped
+// term lo*lo ~ 2^-22), inside the |rel| <= 1e-4 bar.
+//
+// Warp roles (288 threads, one persistent CTA per SM):
+//   warps 0-3  epilogue: tcgen05.ld accumulators -> registers -> bias -> global
+//   warp  4    MMA issuer (one elected lane), TMEM allocator
+//   warps 5-8  producers: global CHW fp32 -> hi/lo split -> shared memory
+// Two shared-memory stages and two TMEM accumulator stages, mbarrier
+// full/empty pairs (tcgen05.commit arrives on the "empty"/"full" barriers).
+// Measured operand-fetch bound of this instruction shape: (M+N)/4 cycles per
+// MMA (128 B/clk of shared-memory operand bandwidth).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace pb {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void fence_async_proxy() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+constexpr uint32_t make_idesc(int M, int N) {
+  // c=F32 (bit 4), a=b=TF32 (bits 7,10), K-major A and B, N>>3 @17, M>>4 @24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+struct KBlock {
+  int first, second;  // chunk ids (tap*CH + c); second == -1: zero-weight dummy
+  int off;            // A start offset of `first`, 16-byte units (= pixels)
+  int lbo;            // A distance first -> second, 16-byte units
+};
+
+template <int IC_, int OC_, int W_, int H_, int F_, bool BWD_>
+struct UCfg {
+  static constexpr int IC = IC_, OC = OC_, W = W_, H = H_, F = F_;
+  static constexpr bool BWD = BWD_;
+  static constexpr int PAD = F / 2;
+  static constexpr int P = W + F - 1;              // shared-memory row pitch, pixels
+  static constexpr int RI = H >= 16 ? 16 : 8;      // output rows per work item
+  static constexpr int SR = RI + F - 1;            // shared-memory rows per item
+  static constexpr int PL = ((SR * P + 7) / 8) * 8;  // pixels per chunk plane
+  static constexpr int CH = (IC + 3) / 4;          // 4-channel chunks
+  static constexpr int NCHUNK = F * F * CH;
+  static constexpr int NKB = (NCHUNK + 1) / 2;     // K=8 blocks
+  static constexpr int MT = RI * 8;                // MMA M: 8-pixel strip x RI rows
+  static constexpr int NT = W / 8;                 // strips (tiles) per item
+  static constexpr int NP = ((OC + 7) / 8) * 8;    // rows of the hi (and lo) weight block
+  static constexpr int N1 = ((2 * NP + 15) / 16) * 16;
+  static constexpr int N2 = MT == 128 ? ((NP + 15) / 16) * 16 : NP;
+  static constexpr int A_STAGE = 2 * CH * PL;      // float4 per stage: hi planes, lo planes
+  static constexpr int B_UNITS = NKB * 2 * N1;     // float4
+  static constexpr int IPS = H / RI;               // items per sample
+  static constexpr int TMEM_STAGE = 128;           // accumulator columns per stage
+  static constexpr size_t SMEM = 16 * (size_t)(2 * A_STAGE + B_UNITS) + 32 * 4 + 8 * 8 + 16;
+  static_assert(W % 8 == 0 && H % RI == 0, "strip tiling");
+  static_assert(NT * N1 <= TMEM_STAGE, "accumulators of one item must fit a TMEM stage");
+  static_assert(N2 <= N1 && N1 % 16 == 0 && N2 % 8 == 0, "MMA N");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+
+  static constexpr int chunk_off(int j) {
+    return ((j / CH) / F) * P + ((j / CH) % F) + (j % CH) * PL;
+  }
+  static constexpr KBlock kblock(int kb) {
+    const int j0 = 2 * kb, j1 = 2 * kb + 1;
+    if (j1 >= NCHUNK) return KBlock{j0, -1, chunk_off(j0), 1};
+    const int o0 = chunk_off(j0), o1 = chunk_off(j1);
+    return o1 > o0 ? KBlock{j0, j1, o0, o1 - o0} : KBlock{j1, j0, o1, o0 - o1};
+  }
+};
+
+template <class C>
+__global__ void __launch_bounds__(288, 1)
+conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
+                 float *__restrict__ Out, int batch) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  float4 *a_s = reinterpret_cast<float4 *>(smem_raw);         // [2][A_STAGE]
+  float4 *b_s = a_s + 2 * C::A_STAGE;                         // [B_UNITS]
+  float *bias_s = reinterpret_cast<float *>(b_s + C::B_UNITS);  // [32]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 32);
+  uint64_t *a_full = bars, *a_empty = bars + 2, *d_full = bars + 4, *d_empty = bars + 6;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int TAPS = C::F * C::F;
+  constexpr int K1 = C::BWD ? TAPS * C::OC + 1 : TAPS * C::IC + 1;  // reference filter-block stride
+
+  // ---- one-time setup -----------------------------------------------------
+  for (int i = tid; i < 2 * C::A_STAGE; i += blockDim.x) a_s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u = tid; u < C::B_UNITS; u += blockDim.x) {
+    const int slot = u / C::N1, n = u - slot * C::N1;
+    const KBlock kb = C::kblock(slot >> 1);
+    const int j = (slot & 1) ? kb.second : kb.first;
+    const bool is_lo = n >= C::NP;
+    const int oc = is_lo ? n - C::NP : n;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j >= 0 && oc < C::OC && n < 2 * C::NP) {
+      const int tap = j / C::CH, c = j - tap * C::CH;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ic = 4 * c + i;
+        if (ic < C::IC) {
+          const float x = C::BWD ? Wt[(int64_t)ic * K1 + oc * TAPS + (TAPS - 1 - tap)]
+                                 : Wt[(int64_t)oc * K1 + ic * TAPS + tap];
+          const float h = tf32_hi(x);
+          w[i] = is_lo ? x - h : h;
+        }
+      }
+    }
+    b_s[u] = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  if (tid < 32) bias_s[tid] = (!C::BWD && tid < C::OC) ? Wt[(int64_t)tid * K1 + K1 - 1] : 0.0f;
+  if (tid == 0) {
+    mbar_init(&a_full[0], 128); mbar_init(&a_full[1], 128);
+    mbar_init(&a_empty[0], 1);  mbar_init(&a_empty[1], 1);
+    mbar_init(&d_full[0], 1);   mbar_init(&d_full[1], 1);
+    mbar_init(&d_empty[0], 128); mbar_init(&d_empty[1], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_ptr)),
+                 "r"(2u * C::TMEM_STAGE)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_proxy();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int n_items = batch * C::IPS;
+
+  if (warp >= 5) {
+    // ---- producers: global CHW -> [chunk][pixel][4] hi / lo ----------------
+    const int ptid = tid - 160;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(&a_empty[s], ph ^ 1);
+      const int b = item / C::IPS, rb = item - b * C::IPS;
+      const int y0 = rb * C::RI - C::PAD;
+      float4 *hi = a_s + s * C::A_STAGE;
+      float4 *lo = hi + C::CH * C::PL;
+      const float *src = In + (int64_t)b * C::IC * C::H * C::W;
+      for (int e = ptid; e < C::CH * C::SR * C::W; e += 128) {
+        const int x = e % C::W;
+        const int t = e / C::W;
+        const int sy = t % C::SR, c = t / C::SR;
+        const int y = y0 + sy;
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ic = 4 * c + i;
+          v[i] = (ic < C::IC && y >= 0 && y < C::H) ? src[(ic * C::H + y) * C::W + x] : 0.0f;
+        }
+        const float h0 = tf32_hi(v[0]), h1 = tf32_hi(v[1]), h2 = tf32_hi(v[2]), h3 = tf32_hi(v[3]);
+        const int pix = c * C::PL + sy * C::P + x + C::PAD;
+        hi[pix] = make_float4(h0, h1, h2, h3);
+        lo[pix] = make_float4(v[0] - h0, v[1] - h1, v[2] - h2, v[3] - h3);
+      }
+      fence_async_proxy();
+      mbar_arrive(&a_full[s]);
+    }
+  } else if (warp == 4) {
+    // ---- MMA issuer ----------------------------------------------------------
+    const bool leader = elect_one();
+    constexpr uint32_t idesc1 = make_idesc(C::MT, C::N1), idesc2 = make_idesc(C::MT, C::N2);
+    constexpr uint32_t a_hi32 = (uint32_t)C::P | (1u << 14);  // SBO = row pitch, version 1
+    constexpr uint32_t b_hi32 = 8u | (1u << 14);              // SBO = 128 B
+    const uint32_t b_lo32 = (smem_u32(b_s) >> 4) | ((uint32_t)C::N1 << 16);  // LBO = N1 rows
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(&a_full[s], ph);
+      mbar_wait(&d_empty[s], ph ^ 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t a_stage = (smem_u32(a_s) >> 4) + (uint32_t)(s * C::A_STAGE);
+#pragma unroll 1
+        for (int tile = 0; tile < C::NT; ++tile) {
+          const uint32_t a_hi_base = a_stage + (uint32_t)(tile * 8);
+          const uint32_t a_lo_base = a_hi_base + (uint32_t)(C::CH * C::PL);
+          const uint32_t d = tmem_base + (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
+#pragma unroll
+          for (int kb = 0; kb < C::NKB; ++kb) {
+            const KBlock k = C::kblock(kb);
+            const uint32_t ak = (uint32_t)k.off | ((uint32_t)k.lbo << 16);
+            const uint64_t db = ((uint64_t)b_hi32 << 32) | (uint64_t)(b_lo32 + (uint32_t)(kb * 2 * C::N1));
+            const uint64_t da_hi = ((uint64_t)a_hi32 << 32) | (uint64_t)(a_hi_base + ak);
+            const uint64_t da_lo = ((uint64_t)a_hi32 << 32) | (uint64_t)(a_lo_base + ak);
+            umma_tf32(d, da_hi, db, idesc1, kb > 0);
+            umma_tf32(d, da_lo, db, idesc2, 1);
+          }
+        }
+        umma_commit(&a_empty[s]);
+        umma_commit(&d_full[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue: TMEM -> registers -> (+bias) -> global ---------------------
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(&d_full[s], ph);
+      tc_fence_after();
+      const int b = item / C::IPS, rb = item - b * C::IPS;
+      // MT=128: TMEM lane = tile row.  MT=64: row i sits in lane 32*(i/16) + i%16.
+      const int row = C::MT == 128 ? warp * 32 + lane : warp * 16 + lane;
+      const bool row_ok = C::MT == 128 || lane < 16;
+      const int r = rb * C::RI + (row >> 3), xin = row & 7;
+#pragma unroll 1
+      for (int tile = 0; tile < C::NT; ++tile) {
+        float v[C::N1];
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
+#pragma unroll
+        for (int q = 0; q < C::N1 / 16; ++q) tmem_ld16(taddr + q * 16, v + q * 16);
+        tmem_ld_wait();
+        if (row_ok) {
+          float *dst = Out + (((int64_t)b * C::OC) * C::H + r) * C::W + tile * 8 + xin;
+#pragma unroll
+          for (int f = 0; f < C::OC; ++f)
+            dst[(int64_t)f * C::H * C::W] = (v[f] + v[C::NP + f]) + bias_s[f];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&d_empty[s]);
+    }
+  }
+
+  // ---- teardown ------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(2u * C::TMEM_STAGE)
+                 : "memory");
+  }
+}
+
+template <class C>
+int launch_umma(pb_context *ctx, const float *In, const float *Wt, float *Out, int64_t batch) {
+  auto kern = conv_umma_kernel<C>;
+  static bool configured = false;
+  if (!configured) {
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    configured = true;
+  }
+  const int64_t n_items = batch * C::IPS;
+  const int grid = (int)std::min<int64_t>(n_items, ctx->num_sms);
+  kern<<<grid, 288, C::SMEM, ctx->stream>>>(In, Wt, Out, (int)batch);
+  PB_LAUNCHED(ctx);
+  return 0;
+}
+
+bool umma_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("PB_DISABLE_UMMA");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
+}  // namespace
+
+// Returns -1 when the shape is outside the tensor-core kernels' envelope.
+int conv_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
+                       float *O, int64_t batch) {
+  if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
+  if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
+  if (l->width != l->height) return -1;
+  const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
+  if (w == 32 && d == 3 && f == 16) return launch_umma<UCfg<3, 16, 32, 32, 5, false>>(ctx, I, W, O, batch);
+  if (w == 16 && d == 16 && f == 20) return launch_umma<UCfg<16, 20, 16, 16, 5, false>>(ctx, I, W, O, batch);
+  if (w == 8 && d == 20 && f == 20) return launch_umma<UCfg<20, 20, 8, 8, 5, false>>(ctx, I, W, O, batch);
+  return -1;
+}
+
+int conv_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, const float *W, const float *G,
+                          float *dI, int64_t batch) {
+  if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
+  if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
+  if (l->width != l->height) return -1;
+  const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
+  if (w == 32 && d == 3 && f == 16) return launch_umma<UCfg<16, 3, 32, 32, 5, true>>(ctx, G, W, dI, batch);
+  if (w == 16 && d == 16 && f == 20) return launch_umma<UCfg<20, 16, 16, 16, 5, true>>(ctx, G, W, dI, batch);
+  if (w == 8 && d == 20 && f == 20) return launch_umma<UCfg<20, 20, 8, 8, 5, true>>(ctx, G, W, dI, batch);
+  return -1;
+}
+
+}  // namespace pb

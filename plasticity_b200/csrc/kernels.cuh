@@ -46,6 +46,13 @@ int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const floa
                              const float *W, const float *G, float *out, const float *lr,
                              int mode, int64_t batch);
 
+// conv_umma.cu: 3xTF32 tcgen05 implicit-GEMM kernels for the batched CIFAR
+// shapes; return -1 outside their envelope.
+int conv_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
+                       float *O, int64_t batch);
+int conv_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, const float *W, const float *G,
+                          float *dI, int64_t batch);
+
 // Output extent of a convolution, nnet/convolution_layer.cc:36-44.
 static inline int64_t conv_out_w(const pb_layer_desc *l) {
   return (l->width - l->filter_width + 2 * l->padding) / l->stride + 1;
