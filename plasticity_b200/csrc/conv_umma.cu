@@ -180,10 +180,12 @@ struct UCfg {
   }
 };
 
-template <class C>
+// ACT >= 0: fused epilogue — additionally writes Out2 = 2x2 max-pool of
+// act(conv output) (MaxPoolLayer forward of ActivationLayer forward).
+template <class C, int ACT>
 __global__ void __launch_bounds__(288, 1)
 conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
-                 float *__restrict__ Out, int batch) {
+                 float *__restrict__ Out, float *__restrict__ Out2, int batch) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float4 *a_s = reinterpret_cast<float4 *>(smem_raw);         // [2][A_STAGE]
   float4 *b_s = a_s + 2 * C::A_STAGE;                         // [B_UNITS]
@@ -329,11 +331,25 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
 #pragma unroll
         for (int q = 0; q < C::N1 / 16; ++q) tmem_ld16(taddr + q * 16, v + q * 16);
         tmem_ld_wait();
+#pragma unroll
+        for (int f = 0; f < C::OC; ++f) v[f] = (v[f] + v[C::NP + f]) + bias_s[f];
         if (row_ok) {
           float *dst = Out + (((int64_t)b * C::OC) * C::H + r) * C::W + tile * 8 + xin;
 #pragma unroll
-          for (int f = 0; f < C::OC; ++f)
-            dst[(int64_t)f * C::H * C::W] = (v[f] + v[C::NP + f]) + bias_s[f];
+          for (int f = 0; f < C::OC; ++f) dst[(int64_t)f * C::H * C::W] = v[f];
+        }
+        if (ACT >= 0) {
+          // 2x2 window partners: x^1 is lane^1, row^1 is lane^8 (row groups of 8 lanes)
+          const bool writer = row_ok && !(lane & 1) && !(lane & 8);
+          float *dst2 = Out2 + (((int64_t)b * C::OC) * (C::H / 2) + (r >> 1)) * (C::W / 2) +
+                        ((tile * 8 + xin) >> 1);
+#pragma unroll
+          for (int f = 0; f < C::OC; ++f) {
+            float m = act_fwd<(ACT >= 0 ? ACT : 0)>(v[f]);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            if (writer) dst2[(int64_t)f * (C::H / 2) * (C::W / 2)] = m;
+          }
         }
       }
       tc_fence_before();
@@ -351,9 +367,10 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   }
 }
 
-template <class C>
-int launch_umma(pb_context *ctx, const float *In, const float *Wt, float *Out, int64_t batch) {
-  auto kern = conv_umma_kernel<C>;
+template <class C, int ACT = -1>
+int launch_umma(pb_context *ctx, const float *In, const float *Wt, float *Out, int64_t batch,
+                float *Out2 = nullptr) {
+  auto kern = conv_umma_kernel<C, ACT>;
   static bool configured = false;
   if (!configured) {
     PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
@@ -361,7 +378,7 @@ int launch_umma(pb_context *ctx, const float *In, const float *Wt, float *Out, i
   }
   const int64_t n_items = batch * C::IPS;
   const int grid = (int)std::min<int64_t>(n_items, ctx->num_sms);
-  kern<<<grid, 288, C::SMEM, ctx->stream>>>(In, Wt, Out, (int)batch);
+  kern<<<grid, 288, C::SMEM, ctx->stream>>>(In, Wt, Out, Out2, (int)batch);
   PB_LAUNCHED(ctx);
   return 0;
 }
@@ -386,6 +403,34 @@ int conv_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, 
   if (w == 32 && d == 3 && f == 16) return launch_umma<UCfg<3, 16, 32, 32, 5, false>>(ctx, I, W, O, batch);
   if (w == 16 && d == 16 && f == 20) return launch_umma<UCfg<16, 20, 16, 16, 5, false>>(ctx, I, W, O, batch);
   if (w == 8 && d == 20 && f == 20) return launch_umma<UCfg<20, 20, 8, 8, 5, false>>(ctx, I, W, O, batch);
+  return -1;
+}
+
+template <class C>
+static int launch_fused(pb_context *ctx, int act, const float *I, const float *W, float *O,
+                        float *O2, int64_t batch) {
+  switch (act) {
+    case PB_IDENTITY: return launch_umma<C, PB_IDENTITY>(ctx, I, W, O, batch, O2);
+    case PB_RELU: return launch_umma<C, PB_RELU>(ctx, I, W, O, batch, O2);
+    case PB_LEAKY_RELU: return launch_umma<C, PB_LEAKY_RELU>(ctx, I, W, O, batch, O2);
+    case PB_SIGMOID: return launch_umma<C, PB_SIGMOID>(ctx, I, W, O, batch, O2);
+  }
+  return -1;
+}
+
+int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, int act,
+                                const pb_layer_desc *pool, const float *I, const float *W,
+                                float *O, float *O2, int64_t batch) {
+  if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
+  if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
+  if (l->width != l->height) return -1;
+  const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
+  if (pool->width != w || pool->height != w || pool->depth != f || pool->out_width * 2 != w ||
+      pool->out_height * 2 != w)
+    return -1;
+  if (w == 32 && d == 3 && f == 16) return launch_fused<UCfg<3, 16, 32, 32, 5, false>>(ctx, act, I, W, O, O2, batch);
+  if (w == 16 && d == 16 && f == 20) return launch_fused<UCfg<16, 20, 16, 16, 5, false>>(ctx, act, I, W, O, O2, batch);
+  if (w == 8 && d == 20 && f == 20) return launch_fused<UCfg<20, 20, 8, 8, 5, false>>(ctx, act, I, W, O, O2, batch);
   return -1;
 }
 

@@ -16,29 +16,6 @@ namespace pb {
 // ---- activation -----------------------------------------------------------
 
 template <int ACT>
-__device__ __forceinline__ float act_fwd(float x) {
-  if (ACT == PB_RELU) return (x >= 0.0f) ? x : 0.0f;
-  if (ACT == PB_LEAKY_RELU) return (x >= 0.0f) ? x : x / 10.0f;
-  if (ACT == PB_SIGMOID) return 1.0f / (1.0f + ref_exp(-x));
-  return x;
-}
-
-// d/dx as the reference's symbolic Derive() prints it: relu (x>=0 ? 1 : 0),
-// leaky (x>=0 ? 1 : 10/100), sigmoid p/((1+p)(1+p)) with p = 2.71828^-x
-// recomputed from the INPUT (not the output).
-template <int ACT>
-__device__ __forceinline__ float act_bwd(float x, float g) {
-  if (ACT == PB_RELU) return g * ((x >= 0.0f) ? 1.0f : 0.0f);
-  if (ACT == PB_LEAKY_RELU) return g * ((x >= 0.0f) ? 1.0f : 0.1f);
-  if (ACT == PB_SIGMOID) {
-    const float p = ref_exp(-x);
-    const float q = 1.0f + p;
-    return g * (p / (q * q));
-  }
-  return g * 1.0f;
-}
-
-template <int ACT>
 __global__ void act_fwd_kernel(const float *__restrict__ I, float *__restrict__ O,
                                int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -217,6 +194,66 @@ int pool_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *I,
   pool_bwd_kernel<<<pb_ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(
       I, G, dI, (int)l->width, (int)l->height, (int)l->depth, (int)l->out_width,
       (int)l->out_height, total);
+  PB_LAUNCHED(ctx);
+  return 0;
+}
+
+// ---- fused activation + 2x2 max-pool backward -------------------------------
+// dO[x] = act'(O[x]) * (act(O[x]) is a maximum of its 2x2 window ? Gp[window] : 0)
+// == activation_input_delta(pool_input_delta(...)) of the unfused path, value
+// for value, without materialising the activation output or the pool's input
+// gradient.  A thread owns two windows (2 rows x 4 columns): float4 loads.
+template <int ACT>
+__global__ void act_pool_bwd_kernel(const float *__restrict__ O, const float *__restrict__ Gp,
+                                    float *__restrict__ dO, int W, int H, int64_t total) {
+  const int wq = W >> 2, oh = H >> 1, ow = W >> 1;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int xq = (int)(t % wq);
+    const int64_t u = t / wq;
+    const int orow = (int)(u % oh);
+    const int64_t bz = u / oh;
+    const int64_t base = bz * H * W + (int64_t)(2 * orow) * W + 4 * xq;
+    const float4 o0 = *reinterpret_cast<const float4 *>(O + base);
+    const float4 o1 = *reinterpret_cast<const float4 *>(O + base + W);
+    const float2 g = *reinterpret_cast<const float2 *>(Gp + bz * oh * ow + (int64_t)orow * ow + 2 * xq);
+    const float a00 = act_fwd<ACT>(o0.x), a01 = act_fwd<ACT>(o0.y), a02 = act_fwd<ACT>(o0.z),
+                a03 = act_fwd<ACT>(o0.w);
+    const float a10 = act_fwd<ACT>(o1.x), a11 = act_fwd<ACT>(o1.y), a12 = act_fwd<ACT>(o1.z),
+                a13 = act_fwd<ACT>(o1.w);
+    const float m0 = fmaxf(fmaxf(a00, a01), fmaxf(a10, a11));
+    const float m1 = fmaxf(fmaxf(a02, a03), fmaxf(a12, a13));
+    float4 d0, d1;
+    d0.x = act_bwd<ACT>(o0.x, a00 < m0 ? 0.0f : g.x);
+    d0.y = act_bwd<ACT>(o0.y, a01 < m0 ? 0.0f : g.x);
+    d0.z = act_bwd<ACT>(o0.z, a02 < m1 ? 0.0f : g.y);
+    d0.w = act_bwd<ACT>(o0.w, a03 < m1 ? 0.0f : g.y);
+    d1.x = act_bwd<ACT>(o1.x, a10 < m0 ? 0.0f : g.x);
+    d1.y = act_bwd<ACT>(o1.y, a11 < m0 ? 0.0f : g.x);
+    d1.z = act_bwd<ACT>(o1.z, a12 < m1 ? 0.0f : g.y);
+    d1.w = act_bwd<ACT>(o1.w, a13 < m1 ? 0.0f : g.y);
+    *reinterpret_cast<float4 *>(dO + base) = d0;
+    *reinterpret_cast<float4 *>(dO + base + W) = d1;
+  }
+}
+
+// Returns -1 when the block is not a (any activation, exact 2x2 pool) pair the
+// fused kernel covers.
+int act_pool_input_delta(pb_context *ctx, int act, const pb_layer_desc *pool, const float *O,
+                         const float *Gp, float *dO, int64_t batch) {
+  const int W = (int)pool->width, H = (int)pool->height;
+  if (pool->out_width * 2 != W || pool->out_height * 2 != H || (W & 3)) return -1;
+  if (!aligned16(O) || !aligned16(dO) || (((uintptr_t)Gp) & 7)) return -1;
+  const int64_t total = batch * pool->depth * (H / 2) * (W / 4);
+  if (total == 0) return 0;
+  const int grid = pb_ew_grid(ctx, total, 256);
+  switch (act) {
+    case PB_IDENTITY: act_pool_bwd_kernel<PB_IDENTITY><<<grid, 256, 0, ctx->stream>>>(O, Gp, dO, W, H, total); break;
+    case PB_RELU: act_pool_bwd_kernel<PB_RELU><<<grid, 256, 0, ctx->stream>>>(O, Gp, dO, W, H, total); break;
+    case PB_LEAKY_RELU: act_pool_bwd_kernel<PB_LEAKY_RELU><<<grid, 256, 0, ctx->stream>>>(O, Gp, dO, W, H, total); break;
+    case PB_SIGMOID: act_pool_bwd_kernel<PB_SIGMOID><<<grid, 256, 0, ctx->stream>>>(O, Gp, dO, W, H, total); break;
+    default: return -1;
+  }
   PB_LAUNCHED(ctx);
   return 0;
 }

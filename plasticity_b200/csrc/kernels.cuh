@@ -18,6 +18,9 @@ int softmax_evaluate(pb_context *ctx, int64_t n, const float *I, float *O, int64
 int softmax_input_delta(pb_context *ctx, int64_t n, const float *I, const float *G,
                         float *dI, int64_t batch);
 
+int act_pool_input_delta(pb_context *ctx, int act, const pb_layer_desc *pool, const float *O,
+                         const float *Gp, float *dO, int64_t batch);
+
 // dense.cu
 int dense_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
                    float *O, int64_t batch);
@@ -52,6 +55,11 @@ int conv_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, 
                        float *O, int64_t batch);
 int conv_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, const float *W, const float *G,
                           float *dI, int64_t batch);
+// convolution + activation + 2x2 max pool in one kernel: writes the convolution
+// output (pre-activation, needed by back-prop) and the pooled output.
+int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *conv, int act,
+                                const pb_layer_desc *pool, const float *I, const float *W,
+                                float *O_conv, float *O_pool, int64_t batch);
 
 // Output extent of a convolution, nnet/convolution_layer.cc:36-44.
 static inline int64_t conv_out_w(const pb_layer_desc *l) {
@@ -67,6 +75,30 @@ __device__ __forceinline__ void apply_update(int mode, float *out, const float *
   if (mode == PB_NEW_WEIGHTS) out[idx] = W[idx] - lr * g;
   else if (mode == PB_WEIGHT_DELTAS) out[idx] = -lr * g;
   else out[idx] += -lr * g;
+}
+
+// ---- activation functions (symbolic/symbolic_util.cc:10-28) ---------------------
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float x) {
+  if (ACT == PB_RELU) return (x >= 0.0f) ? x : 0.0f;
+  if (ACT == PB_LEAKY_RELU) return (x >= 0.0f) ? x : x / 10.0f;
+  if (ACT == PB_SIGMOID) return 1.0f / (1.0f + ref_exp(-x));
+  return x;
+}
+
+// d/dx as the reference's symbolic Derive() prints it: relu (x>=0 ? 1 : 0),
+// leaky (x>=0 ? 1 : 10/100), sigmoid p/((1+p)(1+p)) with p = 2.71828^-x
+// recomputed from the INPUT (not the output).
+template <int ACT>
+__device__ __forceinline__ float act_bwd(float x, float g) {
+  if (ACT == PB_RELU) return g * ((x >= 0.0f) ? 1.0f : 0.0f);
+  if (ACT == PB_LEAKY_RELU) return g * ((x >= 0.0f) ? 1.0f : 0.1f);
+  if (ACT == PB_SIGMOID) {
+    const float p = ref_exp(-x);
+    const float q = 1.0f + p;
+    return g * (p / (q * q));
+  }
+  return g * 1.0f;
 }
 
 }  // namespace pb

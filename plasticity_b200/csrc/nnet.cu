@@ -33,6 +33,14 @@ struct pb_nnet {
   float *stage_in = nullptr, *stage_exp = nullptr;
   cudaGraphExec_t train_exec = nullptr;
   uint64_t graph_launches = 0;  // kernels inside one replay of train_exec
+  // Fused plan of the batched gradient pass (pb_nnet_batch_gradients):
+  //   block[l] != 0: layers l (convolution), l+1 (activation), l+2 (exact 2x2 max
+  //   pool) run as one forward kernel and one elementwise backward kernel;
+  //   alias_input: layer 0 is the Identity input layer (architecture.h:45-47), a
+  //   pure copy forward and backward — the next layer reads the caller's buffer.
+  std::vector<char> block;
+  bool alias_input = false;
+  bool fuse = true;
 };
 
 namespace pb {
@@ -69,6 +77,78 @@ __global__ void fetch_sample_kernel(const pb_nnet::Cursor *__restrict__ cur,
 }
 
 __global__ void advance_cursor_kernel(pb_nnet::Cursor *cur) { cur->idx += 1; }
+
+// Batched forward of the gradient pass with the fused plan.  layer_in[l] is
+// what layer l read (outputs of skipped layers are not materialised).
+static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
+                         std::vector<const float *> &layer_in, std::vector<char> &fused_fwd) {
+  const int n = (int)net->layers.size();
+  const float *cur = d_in;
+  layer_in.assign(n, nullptr);
+  fused_fwd.assign(n, 0);
+  for (int l = 0; l < n; ++l) {
+    layer_in[l] = cur;
+    if (l == 0 && net->alias_input && n > 1) continue;  // identity copy elided
+    const float *W = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
+    if (net->block[l]) {
+      const int rc = conv_act_pool_evaluate_umma(net->ctx, &net->layers[l],
+                                                 net->layers[l + 1].activation,
+                                                 &net->layers[l + 2], cur, W, net->outputs[l],
+                                                 net->outputs[l + 2], batch);
+      if (rc > 0) return 1;
+      if (rc == 0) {
+        fused_fwd[l] = 1;
+        layer_in[l + 1] = net->outputs[l];
+        layer_in[l + 2] = nullptr;  // activation output not materialised
+        cur = net->outputs[l + 2];
+        l += 2;
+        continue;
+      }
+    }
+    if (pb_layer_evaluate(net->ctx, &net->layers[l], cur, W, net->outputs[l], batch)) return 1;
+    cur = net->outputs[l];
+  }
+  return 0;
+}
+
+// Reverse loop over the fused plan; same per-layer order as backward().
+static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool first_chunk,
+                          const std::vector<const float *> &layer_in,
+                          const std::vector<char> &fused_fwd) {
+  const int n = (int)net->layers.size();
+  for (int l = n - 1; l >= 0; --l) {
+    const pb_layer_desc *L = &net->layers[l];
+    if (l == 0 && net->alias_input && n > 1) break;  // dE/dInput == g, unobserved here
+    if (l >= 2 && net->block[l - 2] && L->kind == PB_MAX_POOL) {
+      // pool + activation backward in one pass over the convolution output
+      const int rc = act_pool_input_delta(net->ctx, net->layers[l - 1].activation, L,
+                                          net->outputs[l - 2], g, ng, batch);
+      if (rc > 0) return 1;
+      if (rc == 0) {
+        float *t = g; g = ng; ng = t;
+        l -= 1;  // the activation layer is done too
+        continue;
+      }
+      if (fused_fwd[l - 2]) {
+        // forward skipped the activation output this path needs: recompute it
+        if (pb_layer_evaluate(net->ctx, &net->layers[l - 1], net->outputs[l - 2], nullptr,
+                              net->outputs[l - 1], batch))
+          return 1;
+      }
+    }
+    const float *in = layer_in[l] ? layer_in[l] : net->outputs[l - 1];
+    float *W = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
+    if (pb_layer_input_delta(net->ctx, L, in, W, g, ng, batch)) return 1;
+    if (net->nw[l] > 0) {
+      const int m = first_chunk ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
+      if (pb_layer_weight_update(net->ctx, L, in, W, g, net->deltas + net->w_off[l], net->lr, m,
+                                 batch))
+        return 1;
+    }
+    float *t = g; g = ng; ng = t;
+  }
+  return 0;
+}
 
 static int forward(pb_nnet *net, const float *d_in, int64_t batch) {
   const float *cur = d_in;
@@ -168,6 +248,21 @@ int pb_nnet_create(pb_context *ctx, const pb_layer_desc *layers, int32_t n_layer
     // Keep every layer's weight block 16-byte aligned inside the flat buffer.
     net->total_w += (c + 3) & ~int64_t(3);
     net->max_io = std::max(net->max_io, std::max(a, b));
+  }
+  {
+    const char *e = getenv("PB_DISABLE_FUSION");
+    net->fuse = !(e && e[0] == '1');
+    net->block.assign(n_layers, 0);
+    net->alias_input = net->fuse && layers[0].kind == PB_ACTIVATION &&
+                       layers[0].activation == PB_IDENTITY;
+    for (int l = 0; net->fuse && l + 2 < n_layers; ++l) {
+      const pb_layer_desc &c = layers[l], &a = layers[l + 1], &p = layers[l + 2];
+      if (c.kind != PB_CONVOLUTION || a.kind != PB_ACTIVATION || p.kind != PB_MAX_POOL) continue;
+      if (p.width != pb::conv_out_w(&c) || p.height != pb::conv_out_h(&c) ||
+          p.depth != c.num_filters || p.out_width * 2 != p.width || p.out_height * 2 != p.height)
+        continue;
+      net->block[l] = 1;
+    }
   }
   auto dalloc = [&](float **p, int64_t n) {
     return cudaMalloc((void **)p, sizeof(float) * (size_t)std::max<int64_t>(n, 4));
@@ -378,6 +473,17 @@ int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_exp
   for (int64_t b0 = 0; b0 < batch; b0 += net->max_batch) {
     const int64_t nb = std::min(net->max_batch, batch - b0);
     const float *in = d_ins + b0 * nin;
+    if (net->fuse) {
+      std::vector<const float *> layer_in;
+      std::vector<char> fused_fwd;
+      if (pb::forward_fused(net, in, nb, layer_in, fused_fwd)) return 1;
+      if (pb_error_gradients(ctx, net->loss, nout, net->outputs.back(), d_expected + b0 * nout,
+                             net->grad_a, nb))
+        return 1;
+      if (pb::backward_fused(net, nb, net->grad_a, net->grad_b, b0 == 0, layer_in, fused_fwd))
+        return 1;
+      continue;
+    }
     if (pb::forward(net, in, nb)) return 1;
     if (pb_error_gradients(ctx, net->loss, nout, net->outputs.back(), d_expected + b0 * nout,
                            net->grad_a, nb))

@@ -220,3 +220,30 @@ def test_network_batch_train_and_loop(ctx, name):
     net.TrainLoop(dx, de, 3)
     net.TrainLoop(pb.ClBuffer(xs[3:].reshape(-1)), pb.ClBuffer(es[3:].reshape(-1)), B - 3)
     util.assert_close(util.read_product_weights(net, S), w_ref, f"{name} TrainLoop {B} steps")
+
+
+@pytest.mark.parametrize("name", ["cifar", "mixed", "cifar_grad"])
+def test_batch_train_fused_plan(ctx, name):
+    """BatchTrain at a batch large enough for the tensor-core convolution and the
+    fused conv+activation+pool plan (and its chunked variant), three consecutive
+    steps, against the oracle's gradient-sum step."""
+    spec = po.spec_text(name)
+    S = po.RestatedNet(spec)
+    R = checker(name)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 4242)
+    w0 = util.xavier_like(S, rng)
+    B = 64
+    xs = util.f32(rng.normal(0, 1, (3, B, S.n_in)))
+    es = util.f32(rng.uniform(0, 1, (3, B, S.n_out)))
+    lr = 0.002
+    for max_batch in (B, 40):
+        net = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=max_batch)
+        net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+        util.load_product_weights(net, S, w0)
+        w_ref = w0.copy()
+        for step in range(3):
+            R.batch_train(xs[step].copy(), es[step].copy(), w_ref, lr)
+            net.BatchTrain(net.MakeBuffer(xs[step].reshape(-1)), net.MakeBuffer(es[step].reshape(-1)), B)
+            util.assert_close(util.read_product_weights(net, S), w_ref,
+                              f"{name} fused BatchTrain step {step} max_batch={max_batch}")
