@@ -387,6 +387,14 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int n_par
   apply_update(mode, out, Wt, w, lr[0], (s0 + s1) + (s2 + s3));
 }
 
+int reduce_partials_update(pb_context *ctx, const float *partial, int n_partial, int nw,
+                           const float *Wt, float *out, const float *lr, int mode) {
+  wgrad_reduce_kernel<<<pb_div_up(nw, 128), 128, 0, ctx->stream>>>(partial, n_partial, nw, Wt, out,
+                                                                   lr, mode);
+  PB_LAUNCHED(ctx);
+  return 0;
+}
+
 template <int FW, int FH, int TF>
 static int launch_wgrad(pb_context *ctx, const float *I, const float *Wt, const float *G,
                         float *out, const float *lr, int mode, WgGeom g) {

@@ -231,6 +231,10 @@ int dense_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
   const int64_t in = l->in, nout = l->out;
   const int64_t nw = (in + 1) * nout;
   if (nw == 0) return 0;
+  {
+    const int rc = dense_weight_update_skinny(ctx, l, I, W, G, out, lr, mode, batch);
+    if (rc >= 0) return rc;
+  }
   if (batch <= kGemvMaxBatch) {
     dense_wupd_small_kernel<<<pb_ew_grid(ctx, nw, 256), 256, 0, ctx->stream>>>(
         I, W, G, out, lr, (int)in, (int)nout, batch, mode);

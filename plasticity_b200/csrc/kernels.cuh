@@ -30,6 +30,18 @@ int dense_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
                         const float *W, const float *G, float *out, const float *lr,
                         int mode, int64_t batch);
 
+// head.cu: fused dense -> activation -> softmax -> error-gradient head (forward and
+// backward in one launch) and the skinny dense weight gradient; -1 outside the envelope.
+int head_forward_backward(pb_context *ctx, const pb_layer_desc *dense, int act, int64_t softmax_n,
+                          int loss, const float *X, const float *W, const float *E, float *Z,
+                          float *A, float *Y, float *Gz, float *dX, int64_t batch);
+int dense_weight_update_skinny(pb_context *ctx, const pb_layer_desc *l, const float *X,
+                               const float *W, const float *G, float *out, const float *lr,
+                               int mode, int64_t batch);
+// conv_tiled.cu: out (=|+=) [W] - lr * sum_p partial[p][w], fixed summation order.
+int reduce_partials_update(pb_context *ctx, const float *partial, int n_partial, int nw,
+                           const float *Wt, float *out, const float *lr, int mode);
+
 // conv.cu
 int conv_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
                   float *O, int64_t batch);

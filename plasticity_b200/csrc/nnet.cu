@@ -38,7 +38,11 @@ struct pb_nnet {
   //   pool) run as one forward kernel and one elementwise backward kernel;
   //   alias_input: layer 0 is the Identity input layer (architecture.h:45-47), a
   //   pure copy forward and backward — the next layer reads the caller's buffer.
+  //   head: index of the DenseLayer of a trailing dense -> activation -> softmax
+  //   chain (or -1): forward, error gradient and backward of those three layers
+  //   run as one kernel (head.cu).
   std::vector<char> block;
+  int head = -1;
   bool alias_input = false;
   bool fuse = true;
 };
@@ -81,7 +85,8 @@ __global__ void advance_cursor_kernel(pb_nnet::Cursor *cur) { cur->idx += 1; }
 // Batched forward of the gradient pass with the fused plan.  layer_in[l] is
 // what layer l read (outputs of skipped layers are not materialised).
 static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
-                         std::vector<const float *> &layer_in, std::vector<char> &fused_fwd) {
+                         std::vector<const float *> &layer_in, std::vector<char> &fused_fwd,
+                         bool head_ok) {
   const int n = (int)net->layers.size();
   const float *cur = d_in;
   layer_in.assign(n, nullptr);
@@ -89,6 +94,7 @@ static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
   for (int l = 0; l < n; ++l) {
     layer_in[l] = cur;
     if (l == 0 && net->alias_input && n > 1) continue;  // identity copy elided
+    if (l == net->head && head_ok) break;             // the head kernel does the rest
     const float *W = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
     if (net->block[l]) {
       const int rc = conv_act_pool_evaluate_umma(net->ctx, &net->layers[l],
@@ -114,9 +120,9 @@ static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
 // Reverse loop over the fused plan; same per-layer order as backward().
 static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool first_chunk,
                           const std::vector<const float *> &layer_in,
-                          const std::vector<char> &fused_fwd) {
+                          const std::vector<char> &fused_fwd, int top) {
   const int n = (int)net->layers.size();
-  for (int l = n - 1; l >= 0; --l) {
+  for (int l = top; l >= 0; --l) {
     const pb_layer_desc *L = &net->layers[l];
     if (l == 0 && net->alias_input && n > 1) break;  // dE/dInput == g, unobserved here
     if (l >= 2 && net->block[l - 2] && L->kind == PB_MAX_POOL) {
@@ -262,6 +268,14 @@ int pb_nnet_create(pb_context *ctx, const pb_layer_desc *layers, int32_t n_layer
           p.depth != c.num_filters || p.out_width * 2 != p.width || p.out_height * 2 != p.height)
         continue;
       net->block[l] = 1;
+    }
+    // trailing dense -> activation -> softmax (h > 0: the dense layer is never layer 0)
+    if (net->fuse && n_layers >= 4) {
+      const int h = n_layers - 3;
+      if (layers[h].kind == PB_DENSE && layers[h + 1].kind == PB_ACTIVATION &&
+          layers[h + 2].kind == PB_SOFTMAX && layers[h + 2].n == layers[h].out &&
+          layers[h + 1].n == layers[h].out && !net->block[h - 1] && (h < 2 || !net->block[h - 2]))
+        net->head = h;
     }
   }
   auto dalloc = [&](float **p, int64_t n) {
@@ -476,12 +490,45 @@ int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_exp
     if (net->fuse) {
       std::vector<const float *> layer_in;
       std::vector<char> fused_fwd;
-      if (pb::forward_fused(net, in, nb, layer_in, fused_fwd)) return 1;
-      if (pb_error_gradients(ctx, net->loss, nout, net->outputs.back(), d_expected + b0 * nout,
+      const int n = (int)net->layers.size();
+      const int h = net->head;
+      if (pb::forward_fused(net, in, nb, layer_in, fused_fwd, h > 0)) return 1;
+      int top = n - 1;
+      float *g = net->grad_a, *ng = net->grad_b;
+      bool head_done = false;
+      if (h > 0) {
+        // X = what the dense layer reads; Gz (dE/d dense output) goes to `ng`,
+        // dE/dX to `g` — then the dense weight gradient, then the loop below.
+        const float *X = layer_in[h];
+        float *W = net->weights + net->w_off[h];
+        const int rc = pb::head_forward_backward(
+            ctx, &net->layers[h], net->layers[h + 1].activation, net->layers[h + 2].n, net->loss,
+            X, W, d_expected + b0 * nout, net->outputs[h], net->outputs[h + 1],
+            net->outputs[h + 2], ng, g, nb);
+        if (rc > 0) return 1;
+        if (rc == 0) {
+          const int m = b0 == 0 ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
+          if (pb_layer_weight_update(ctx, &net->layers[h], X, W, ng, net->deltas + net->w_off[h],
+                                     net->lr, m, nb))
+            return 1;
+          top = h - 1;
+          head_done = true;
+        } else {
+          // outside the head kernel's envelope: finish the forward pass layer by layer
+          const float *cur = X;
+          for (int l = h; l < n; ++l) {
+            layer_in[l] = cur;
+            const float *Wl = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
+            if (pb_layer_evaluate(ctx, &net->layers[l], cur, Wl, net->outputs[l], nb)) return 1;
+            cur = net->outputs[l];
+          }
+        }
+      }
+      if (!head_done &&
+          pb_error_gradients(ctx, net->loss, nout, net->outputs.back(), d_expected + b0 * nout,
                              net->grad_a, nb))
         return 1;
-      if (pb::backward_fused(net, nb, net->grad_a, net->grad_b, b0 == 0, layer_in, fused_fwd))
-        return 1;
+      if (pb::backward_fused(net, nb, g, ng, b0 == 0, layer_in, fused_fwd, top)) return 1;
       continue;
     }
     if (pb::forward(net, in, nb)) return 1;

@@ -234,16 +234,21 @@ def test_batch_train_fused_plan(ctx, name):
     rng = np.random.default_rng(zlib.crc32(name.encode()) + 4242)
     w0 = util.xavier_like(S, rng)
     B = 64
-    xs = util.f32(rng.normal(0, 1, (3, B, S.n_in)))
     es = util.f32(rng.uniform(0, 1, (3, B, S.n_out)))
     lr = 0.002
+    nets = []
     for max_batch in (B, 40):
         net = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=max_batch)
         net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
         util.load_product_weights(net, S, w0)
-        w_ref = w0.copy()
-        for step in range(3):
-            R.batch_train(xs[step].copy(), es[step].copy(), w_ref, lr)
-            net.BatchTrain(net.MakeBuffer(xs[step].reshape(-1)), net.MakeBuffer(es[step].reshape(-1)), B)
+        nets.append((max_batch, net))
+    w_ref = w0.copy()
+    for step in range(3):
+        # samples whose pool windows have a clear winner under the current weights
+        # (max-pool routing is discontinuous; see util.pool_margin)
+        xs = util.draw_with_pool_margin(S, rng, B, w_ref)
+        R.batch_train(xs.copy(), es[step].copy(), w_ref, lr)
+        for max_batch, net in nets:
+            net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es[step].reshape(-1)), B)
             util.assert_close(util.read_product_weights(net, S), w_ref,
                               f"{name} fused BatchTrain step {step} max_batch={max_batch}")

@@ -89,3 +89,38 @@ def read_product_weights(pnet, onet):
         if onet.nw[l]:
             w[onet.w_off[l]:onet.w_off[l + 1]] = pnet.GetLayerWeights(l)
     return w
+
+
+def pool_margin(onet, x, weights):
+    """Smallest relative gap between the two largest values of any max-pool
+    window of the network evaluated (fp64 oracle) at `x`.  Max-pool routing is a
+    discontinuous function of its inputs: when two window elements agree to
+    ~1e-6 (fp32 / 3xTF32 rounding), the device and the fp64 oracle may route the
+    gradient to different elements, which is a property of finite precision and
+    not of either implementation.  Parity cases are drawn with a margin."""
+    lo = onet.evaluate(np.array(x, dtype=np.float64), np.array(weights, dtype=np.float64))
+    worst = np.inf
+    for l in range(onet.n_layers):
+        L = onet.layers[l]
+        if L.kind != po.KINDS["pool"]:
+            continue
+        v = onet.layer_output(lo, l - 1).reshape(L.D, L.H, L.W)
+        gh, gw = L.H // L.oh, L.W // L.ow
+        v = v[:, :L.oh * gh, :L.ow * gw].reshape(L.D, L.oh, gh, L.ow, gw)
+        win = np.sort(v.transpose(0, 1, 3, 2, 4).reshape(-1, gh * gw), axis=1)
+        if win.shape[1] < 2:
+            continue
+        gap = (win[:, -1] - win[:, -2]) / (np.abs(win[:, -1]) + 1e-3)
+        worst = min(worst, float(gap.min()))
+    return worst
+
+
+def draw_with_pool_margin(onet, rng, n, weights, margin=2e-5, scale=1.0):
+    """n fp32-representable N(0, scale^2) samples whose pool windows all have a
+    top-2 gap of at least `margin` (relative) under `weights`."""
+    out = []
+    while len(out) < n:
+        x = f32(rng.normal(0, scale, onet.n_in))
+        if pool_margin(onet, x, weights) >= margin:
+            out.append(x)
+    return np.stack(out)
