@@ -369,28 +369,38 @@ conv_wgrad_s1_kernel(const float *__restrict__ In, const float *__restrict__ G,
   }
 }
 
-// Deterministic reduction of the per-CTA partial sums + SGD update.
-__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int n_partial, int nw,
-                                    const float *Wt, float *out, const float *__restrict__ lr,
-                                    int mode) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nw) return;
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-  int i = 0;
-  for (; i + 3 < n_partial; i += 4) {
-    s0 += partial[(int64_t)(i + 0) * nw + w];
-    s1 += partial[(int64_t)(i + 1) * nw + w];
-    s2 += partial[(int64_t)(i + 2) * nw + w];
-    s3 += partial[(int64_t)(i + 3) * nw + w];
+// Deterministic reduction of the per-CTA partial sums + SGD update.  A CTA owns
+// 32 weights; its 8 warps each sum every 8th partial (coalesced rows), then one
+// warp adds the 8 sub-sums in a fixed order.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float *__restrict__ partial, int n_partial, int nw, const float *Wt,
+                    float *out, const float *__restrict__ lr, int mode) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int w = blockIdx.x * 32 + lane;
+  float s0 = 0.0f, s1 = 0.0f;
+  if (w < nw) {
+    int i = g;
+    for (; i + 8 < n_partial; i += 16) {
+      s0 += partial[(int64_t)i * nw + w];
+      s1 += partial[(int64_t)(i + 8) * nw + w];
+    }
+    if (i < n_partial) s0 += partial[(int64_t)i * nw + w];
   }
-  for (; i < n_partial; ++i) s0 += partial[(int64_t)i * nw + w];
-  apply_update(mode, out, Wt, w, lr[0], (s0 + s1) + (s2 + s3));
+  red[g][lane] = s0 + s1;
+  __syncthreads();
+  if (g == 0 && w < nw) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += red[k][lane];
+    apply_update(mode, out, Wt, w, lr[0], sum);
+  }
 }
 
 int reduce_partials_update(pb_context *ctx, const float *partial, int n_partial, int nw,
                            const float *Wt, float *out, const float *lr, int mode) {
-  wgrad_reduce_kernel<<<pb_div_up(nw, 128), 128, 0, ctx->stream>>>(partial, n_partial, nw, Wt, out,
-                                                                   lr, mode);
+  wgrad_reduce_kernel<<<pb_div_up(nw, 32), 256, 0, ctx->stream>>>(partial, n_partial, nw, Wt, out,
+                                                                  lr, mode);
   PB_LAUNCHED(ctx);
   return 0;
 }
@@ -431,10 +441,7 @@ static int launch_wgrad(pb_context *ctx, const float *I, const float *Wt, const 
   PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   kern<<<grid, threads, smem, ctx->stream>>>(I, G, ctx->workspace, g);
   PB_LAUNCHED(ctx);
-  wgrad_reduce_kernel<<<pb_div_up(nw, 128), 128, 0, ctx->stream>>>(ctx->workspace, grid, nw, Wt,
-                                                                   out, lr, mode);
-  PB_LAUNCHED(ctx);
-  return 0;
+  return reduce_partials_update(ctx, ctx->workspace, grid, nw, Wt, out, lr, mode);
 }
 
 int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const float *I,

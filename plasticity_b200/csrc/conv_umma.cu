@@ -26,10 +26,10 @@
 // and the epilogue adds the two column groups: fp32-level accuracy (dropped
 // term lo*lo ~ 2^-22), inside the |rel| <= 1e-4 bar.
 //
-// Warp roles (288 threads, one persistent CTA per SM):
+// Warp roles (416 threads, one persistent CTA per SM):
 //   warps 0-3  epilogue: tcgen05.ld accumulators -> registers -> bias -> global
 //   warp  4    MMA issuer (one elected lane), TMEM allocator
-//   warps 5-8  producers: global CHW fp32 -> hi/lo split -> shared memory
+//   warps 5-12 producers: global CHW fp32 -> hi/lo split -> shared memory
 // Two shared-memory stages and two TMEM accumulator stages, mbarrier
 // full/empty pairs (tcgen05.commit arrives on the "empty"/"full" barriers).
 // Measured operand-fetch bound of this instruction shape: (M+N)/4 cycles per
@@ -136,6 +136,10 @@ constexpr uint32_t make_idesc(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// warps 0-3 epilogue, warp 4 MMA issuer, warps 5-12 producers
+constexpr int kProducers = 256;
+constexpr int kThreads = 160 + kProducers;
+
 struct KBlock {
   int first, second;  // chunk ids (tap*CH + c); second == -1: zero-weight dummy
   int off;            // A start offset of `first`, 16-byte units (= pixels)
@@ -183,7 +187,7 @@ struct UCfg {
 // ACT >= 0: fused epilogue — additionally writes Out2 = 2x2 max-pool of
 // act(conv output) (MaxPoolLayer forward of ActivationLayer forward).
 template <class C, int ACT>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
                  float *__restrict__ Out, float *__restrict__ Out2, int batch) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -224,7 +228,7 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   }
   if (tid < 32) bias_s[tid] = (!C::BWD && tid < C::OC) ? Wt[(int64_t)tid * K1 + K1 - 1] : 0.0f;
   if (tid == 0) {
-    mbar_init(&a_full[0], 128); mbar_init(&a_full[1], 128);
+    mbar_init(&a_full[0], kProducers); mbar_init(&a_full[1], kProducers);
     mbar_init(&a_empty[0], 1);  mbar_init(&a_empty[1], 1);
     mbar_init(&d_full[0], 1);   mbar_init(&d_full[1], 1);
     mbar_init(&d_empty[0], 128); mbar_init(&d_empty[1], 128);
@@ -246,31 +250,48 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
 
   if (warp >= 5) {
     // ---- producers: global CHW -> [chunk][pixel][4] hi / lo ----------------
+    // All global loads of an item are issued before the first conversion so the
+    // memory latency is paid once per item, not once per element.
     const int ptid = tid - 160;
+    constexpr int TOTAL = C::CH * C::SR * C::W;
+    constexpr int ITERS = (TOTAL + kProducers - 1) / kProducers;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(&a_empty[s], ph ^ 1);
       const int b = item / C::IPS, rb = item - b * C::IPS;
       const int y0 = rb * C::RI - C::PAD;
       float4 *hi = a_s + s * C::A_STAGE;
       float4 *lo = hi + C::CH * C::PL;
       const float *src = In + (int64_t)b * C::IC * C::H * C::W;
-      for (int e = ptid; e < C::CH * C::SR * C::W; e += 128) {
+      float v[ITERS][4];
+#pragma unroll
+      for (int k = 0; k < ITERS; ++k) {
+        const int e = ptid + k * kProducers;
         const int x = e % C::W;
         const int t = e / C::W;
         const int sy = t % C::SR, c = t / C::SR;
         const int y = y0 + sy;
-        float v[4];
+        const bool ok = e < TOTAL && y >= 0 && y < C::H;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ic = 4 * c + i;
-          v[i] = (ic < C::IC && y >= 0 && y < C::H) ? src[(ic * C::H + y) * C::W + x] : 0.0f;
+          v[k][i] = (ok && ic < C::IC) ? __ldg(src + (ic * C::H + y) * C::W + x) : 0.0f;
         }
-        const float h0 = tf32_hi(v[0]), h1 = tf32_hi(v[1]), h2 = tf32_hi(v[2]), h3 = tf32_hi(v[3]);
-        const int pix = c * C::PL + sy * C::P + x + C::PAD;
-        hi[pix] = make_float4(h0, h1, h2, h3);
-        lo[pix] = make_float4(v[0] - h0, v[1] - h1, v[2] - h2, v[3] - h3);
+      }
+      mbar_wait(&a_empty[s], ph ^ 1);
+#pragma unroll
+      for (int k = 0; k < ITERS; ++k) {
+        const int e = ptid + k * kProducers;
+        if (e < TOTAL) {
+          const int x = e % C::W;
+          const int t = e / C::W;
+          const int sy = t % C::SR, c = t / C::SR;
+          const float h0 = tf32_hi(v[k][0]), h1 = tf32_hi(v[k][1]), h2 = tf32_hi(v[k][2]),
+                      h3 = tf32_hi(v[k][3]);
+          const int pix = c * C::PL + sy * C::P + x + C::PAD;
+          hi[pix] = make_float4(h0, h1, h2, h3);
+          lo[pix] = make_float4(v[k][0] - h0, v[k][1] - h1, v[k][2] - h2, v[k][3] - h3);
+        }
       }
       fence_async_proxy();
       mbar_arrive(&a_full[s]);
@@ -378,7 +399,7 @@ int launch_umma(pb_context *ctx, const float *In, const float *Wt, float *Out, i
   }
   const int64_t n_items = batch * C::IPS;
   const int grid = (int)std::min<int64_t>(n_items, ctx->num_sms);
-  kern<<<grid, 288, C::SMEM, ctx->stream>>>(In, Wt, Out, Out2, (int)batch);
+  kern<<<grid, kThreads, C::SMEM, ctx->stream>>>(In, Wt, Out, Out2, (int)batch);
   PB_LAUNCHED(ctx);
   return 0;
 }
