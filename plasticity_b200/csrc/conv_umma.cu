@@ -146,35 +146,45 @@ struct KBlock {
   int lbo;            // A distance first -> second, 16-byte units
 };
 
-template <int IC_, int OC_, int W_, int H_, int F_, bool BWD_>
+// NS ("N-stacked", for very few output channels): the fx taps are moved from K
+// into N.  The MMA computes, per pixel (r,x'), Q[(fx,oc)] = sum_{fy,ic} W[oc,ic,fy,fx] *
+// In0[ic, r-p+fy, x'] (no horizontal shift), K shrinks F-fold, and the epilogue
+// gathers Out[oc,r,c] = sum_fx Q[(r, c-p+fx)][(fx,oc)] through shared memory.
+template <int IC_, int OC_, int W_, int H_, int F_, bool BWD_, bool NS_ = false>
 struct UCfg {
   static constexpr int IC = IC_, OC = OC_, W = W_, H = H_, F = F_;
-  static constexpr bool BWD = BWD_;
+  static constexpr bool BWD = BWD_, NS = NS_;
+  static constexpr int NOUT = NS ? F * OC : OC;    // GEMM columns (before hi/lo doubling)
   static constexpr int PAD = F / 2;
   static constexpr int P = W + F - 1;              // shared-memory row pitch, pixels
   static constexpr int RI = H >= 16 ? 16 : 8;      // output rows per work item
   static constexpr int SR = RI + F - 1;            // shared-memory rows per item
   static constexpr int PL = ((SR * P + 7) / 8) * 8;  // pixels per chunk plane
   static constexpr int CH = (IC + 3) / 4;          // 4-channel chunks
-  static constexpr int NCHUNK = F * F * CH;
+  static constexpr int NCHUNK = (NS ? F : F * F) * CH;
   static constexpr int NKB = (NCHUNK + 1) / 2;     // K=8 blocks
   static constexpr int MT = RI * 8;                // MMA M: 8-pixel strip x RI rows
   static constexpr int NT = W / 8;                 // strips (tiles) per item
-  static constexpr int NP = ((OC + 7) / 8) * 8;    // rows of the hi (and lo) weight block
+  static constexpr int NP = ((NOUT + 7) / 8) * 8;  // rows of the hi (and lo) weight block
   static constexpr int N1 = ((2 * NP + 15) / 16) * 16;
   static constexpr int N2 = MT == 128 ? ((NP + 15) / 16) * 16 : NP;
   static constexpr int A_STAGE = 2 * CH * PL;      // float4 per stage: hi planes, lo planes
   static constexpr int B_UNITS = NKB * 2 * N1;     // float4
   static constexpr int IPS = H / RI;               // items per sample
   static constexpr int TMEM_STAGE = 128;           // accumulator columns per stage
-  static constexpr size_t SMEM = 16 * (size_t)(2 * A_STAGE + B_UNITS) + 32 * 4 + 8 * 8 + 16;
+  static constexpr int STG_REC = NOUT | 1;         // odd record pitch: conflict-free staging
+  static constexpr int STG_FLOATS = NS ? RI * W * STG_REC : 0;
+  static constexpr size_t SMEM =
+      16 * (size_t)(2 * A_STAGE + B_UNITS) + 32 * 4 + 8 * 8 + 16 + 4 * (size_t)STG_FLOATS;
+  static_assert(!NS || (BWD && MT == 128 && NOUT <= 32), "N-stacked variant envelope");
   static_assert(W % 8 == 0 && H % RI == 0, "strip tiling");
   static_assert(NT * N1 <= TMEM_STAGE, "accumulators of one item must fit a TMEM stage");
   static_assert(N2 <= N1 && N1 % 16 == 0 && N2 % 8 == 0, "MMA N");
   static_assert(SMEM <= 227 * 1024, "shared memory");
 
   static constexpr int chunk_off(int j) {
-    return ((j / CH) / F) * P + ((j / CH) % F) + (j % CH) * PL;
+    return NS ? (j / CH) * P + PAD + (j % CH) * PL
+              : ((j / CH) / F) * P + ((j / CH) % F) + (j % CH) * PL;
   }
   static constexpr KBlock kblock(int kb) {
     const int j0 = 2 * kb, j1 = 2 * kb + 1;
@@ -197,28 +207,39 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 32);
   uint64_t *a_full = bars, *a_empty = bars + 2, *d_full = bars + 4, *d_empty = bars + 6;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 8);
+  float *stg = reinterpret_cast<float *>(tmem_ptr + 4);      // [RI*W][STG_REC] (NS only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int TAPS = C::F * C::F;
   constexpr int K1 = C::BWD ? TAPS * C::OC + 1 : TAPS * C::IC + 1;  // reference filter-block stride
 
   // ---- one-time setup -----------------------------------------------------
-  for (int i = tid; i < 2 * C::A_STAGE; i += blockDim.x) a_s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // Raw filter block (reference layout) -> shared-memory scratch (the A stages,
+  // not yet in use) with coalesced loads, then the hi/lo, chunk-ordered B image
+  // is built from shared memory.
+  constexpr int NWT = (C::BWD ? C::IC : C::OC) * K1;
+  static_assert(NWT <= 8 * C::A_STAGE, "weight scratch must fit the A stages");
+  float *w_raw = reinterpret_cast<float *>(a_s);
+  for (int i = tid; i < NWT; i += blockDim.x) w_raw[i] = Wt[i];
+  __syncthreads();
   for (int u = tid; u < C::B_UNITS; u += blockDim.x) {
     const int slot = u / C::N1, n = u - slot * C::N1;
     const KBlock kb = C::kblock(slot >> 1);
     const int j = (slot & 1) ? kb.second : kb.first;
     const bool is_lo = n >= C::NP;
-    const int oc = is_lo ? n - C::NP : n;
+    const int col = is_lo ? n - C::NP : n;          // GEMM column
     float w[4] = {0.f, 0.f, 0.f, 0.f};
-    if (j >= 0 && oc < C::OC && n < 2 * C::NP) {
-      const int tap = j / C::CH, c = j - tap * C::CH;
+    if (j >= 0 && col < C::NOUT && n < 2 * C::NP) {
+      const int c = j % C::CH;
+      // NS: column = (fx, oc), chunk = (fy, c).  Otherwise column = oc, chunk = (tap, c).
+      const int oc = C::NS ? col % C::OC : col;
+      const int tap = C::NS ? (j / C::CH) * C::F + col / C::OC : j / C::CH;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int ic = 4 * c + i;
         if (ic < C::IC) {
-          const float x = C::BWD ? Wt[(int64_t)ic * K1 + oc * TAPS + (TAPS - 1 - tap)]
-                                 : Wt[(int64_t)oc * K1 + ic * TAPS + tap];
+          const float x = C::BWD ? w_raw[ic * K1 + oc * TAPS + (TAPS - 1 - tap)]
+                                 : w_raw[oc * K1 + ic * TAPS + tap];
           const float h = tf32_hi(x);
           w[i] = is_lo ? x - h : h;
         }
@@ -226,7 +247,9 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
     }
     b_s[u] = make_float4(w[0], w[1], w[2], w[3]);
   }
-  if (tid < 32) bias_s[tid] = (!C::BWD && tid < C::OC) ? Wt[(int64_t)tid * K1 + K1 - 1] : 0.0f;
+  if (tid < 32) bias_s[tid] = (!C::BWD && tid < C::OC) ? w_raw[tid * K1 + K1 - 1] : 0.0f;
+  __syncthreads();
+  for (int i = tid; i < 2 * C::A_STAGE; i += blockDim.x) a_s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
     mbar_init(&a_full[0], kProducers); mbar_init(&a_full[1], kProducers);
     mbar_init(&a_empty[0], 1);  mbar_init(&a_empty[1], 1);
@@ -309,24 +332,28 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
       mbar_wait(&a_full[s], ph);
       mbar_wait(&d_empty[s], ph ^ 1);
       tc_fence_after();
-      if (leader) {
-        const uint32_t a_stage = (smem_u32(a_s) >> 4) + (uint32_t)(s * C::A_STAGE);
+      // Descriptor arithmetic is warp-uniform (uniform datapath); only the
+      // tcgen05 instructions themselves are predicated on the elected lane.
+      const uint32_t a_stage = (smem_u32(a_s) >> 4) + (uint32_t)(s * C::A_STAGE);
 #pragma unroll 1
-        for (int tile = 0; tile < C::NT; ++tile) {
-          const uint32_t a_hi_base = a_stage + (uint32_t)(tile * 8);
-          const uint32_t a_lo_base = a_hi_base + (uint32_t)(C::CH * C::PL);
-          const uint32_t d = tmem_base + (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
+      for (int tile = 0; tile < C::NT; ++tile) {
+        const uint32_t a_hi_base = a_stage + (uint32_t)(tile * 8);
+        const uint32_t a_lo_base = a_hi_base + (uint32_t)(C::CH * C::PL);
+        const uint32_t d = tmem_base + (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
 #pragma unroll
-          for (int kb = 0; kb < C::NKB; ++kb) {
-            const KBlock k = C::kblock(kb);
-            const uint32_t ak = (uint32_t)k.off | ((uint32_t)k.lbo << 16);
-            const uint64_t db = ((uint64_t)b_hi32 << 32) | (uint64_t)(b_lo32 + (uint32_t)(kb * 2 * C::N1));
-            const uint64_t da_hi = ((uint64_t)a_hi32 << 32) | (uint64_t)(a_hi_base + ak);
-            const uint64_t da_lo = ((uint64_t)a_hi32 << 32) | (uint64_t)(a_lo_base + ak);
+        for (int kb = 0; kb < C::NKB; ++kb) {
+          const KBlock k = C::kblock(kb);
+          const uint32_t ak = (uint32_t)k.off | ((uint32_t)k.lbo << 16);
+          const uint64_t db = ((uint64_t)b_hi32 << 32) | (uint64_t)(b_lo32 + (uint32_t)(kb * 2 * C::N1));
+          const uint64_t da_hi = ((uint64_t)a_hi32 << 32) | (uint64_t)(a_hi_base + ak);
+          const uint64_t da_lo = ((uint64_t)a_hi32 << 32) | (uint64_t)(a_lo_base + ak);
+          if (leader) {
             umma_tf32(d, da_hi, db, idesc1, kb > 0);
             umma_tf32(d, da_lo, db, idesc2, 1);
           }
         }
+      }
+      if (leader) {
         umma_commit(&a_empty[s]);
         umma_commit(&d_full[s]);
       }
@@ -344,6 +371,40 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
       const int row = C::MT == 128 ? warp * 32 + lane : warp * 16 + lane;
       const bool row_ok = C::MT == 128 || lane < 16;
       const int r = rb * C::RI + (row >> 3), xin = row & 7;
+      if (C::NS) {
+        // stage Q for the whole item, release TMEM, then gather the fx taps
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's gather is done
+#pragma unroll 1
+        for (int tile = 0; tile < C::NT; ++tile) {
+          float v[C::N1];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                                 (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
+#pragma unroll
+          for (int q = 0; q < C::N1 / 16; ++q) tmem_ld16(taddr + q * 16, v + q * 16);
+          tmem_ld_wait();
+          float *rec = stg + ((row >> 3) * C::W + tile * 8 + xin) * C::STG_REC;
+#pragma unroll
+          for (int n = 0; n < C::NOUT; ++n) rec[n] = v[n] + v[C::NP + n];
+        }
+        tc_fence_before();
+        mbar_arrive(&d_empty[s]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int p = tid; p < C::RI * C::W; p += 128) {
+          const int rl = p / C::W, c = p - rl * C::W;
+          float *dst = Out + (((int64_t)b * C::OC) * C::H + rb * C::RI + rl) * C::W + c;
+#pragma unroll
+          for (int z = 0; z < C::OC; ++z) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int fx = 0; fx < C::F; ++fx) {
+              const int xs = c - C::PAD + fx;
+              if (xs >= 0 && xs < C::W) acc += stg[(rl * C::W + xs) * C::STG_REC + fx * C::OC + z];
+            }
+            dst[(int64_t)z * C::H * C::W] = acc;
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int tile = 0; tile < C::NT; ++tile) {
         float v[C::N1];
@@ -461,7 +522,7 @@ int conv_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, const float *
   if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
   if (l->width != l->height) return -1;
   const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
-  if (w == 32 && d == 3 && f == 16) return launch_umma<UCfg<16, 3, 32, 32, 5, true>>(ctx, G, W, dI, batch);
+  if (w == 32 && d == 3 && f == 16) return launch_umma<UCfg<16, 3, 32, 32, 5, true, true>>(ctx, G, W, dI, batch);
   if (w == 16 && d == 16 && f == 20) return launch_umma<UCfg<20, 16, 16, 16, 5, true>>(ctx, G, W, dI, batch);
   if (w == 8 && d == 20 && f == 20) return launch_umma<UCfg<20, 20, 8, 8, 5, true>>(ctx, G, W, dI, batch);
   return -1;

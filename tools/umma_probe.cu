@@ -276,6 +276,83 @@ static void run_rate(const char *name) {
   cudaFree(d_cyc);
 }
 
+
+// Alternating-shape pairs as the convolution kernel issues them: hi pass (N1)
+// then lo pass (N2) onto the same accumulator columns.
+template <int M, int N1, int N2, int KB>
+__global__ void __launch_bounds__(128, 1) pair_kernel(long long *cycles, int reps) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<float *>(smem)[i] = 0.0f;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  constexpr uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  if (warp == 0) {
+    constexpr uint32_t LBO_A = 6400, LBO_B = N1 * 16, SBO_A = 320;
+    const uint64_t da0 = make_desc(smem_u32(smem), LBO_A, SBO_A);
+    const uint64_t dl0 = make_desc(smem_u32(smem) + 30 * 1024, LBO_A, SBO_A);
+    const uint64_t db0 = make_desc(smem_u32(smem) + 64 * 1024, LBO_B, 128);
+    const bool leader = elect_one();
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint64_t da = da0 + (uint64_t)(kb % 5 + (kb / 5) * 20);
+        const uint64_t dl = dl0 + (uint64_t)(kb % 5 + (kb / 5) * 20);
+        const uint64_t db = db0 + (uint64_t)((kb % 4) * ((2 * LBO_B) >> 4));
+        if (leader) {
+          umma_tf32(tmem_d, da, db, idesc1, 1);
+          umma_tf32(tmem_d, dl, db, idesc2, 1);
+        }
+      }
+    }
+    if (leader) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (tid == 0) cycles[0] = t1 - t0;
+  } else {
+    mbar_wait(&bar, 0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+}
+
+template <int M, int N1, int N2, int KB>
+static void run_pair(const char *name) {
+  long long *d_cyc;
+  CK(cudaMalloc(&d_cyc, sizeof(long long)));
+  auto k = pair_kernel<M, N1, N2, KB>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  long long c[2];
+  const int reps[2] = {16, 144};
+  for (int i = 0; i < 2; ++i) {
+    k<<<1, 128, 100 * 1024>>>(d_cyc, reps[i]);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&c[i], d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  printf("pair %-10s M=%3d N1=%3d N2=%3d KB=%d : %.2f cyc/pair (model %.1f)\n", name, M, N1, N2, KB,
+         (double)(c[1] - c[0]) / (128.0 * KB), (M + N1) / 4.0 + (M + N2) / 4.0);
+  cudaFree(d_cyc);
+}
+
 struct Case {
   const char *name;
   int M, N, KB, sbo_a, shift, rows_a;  // rows_a: rows present in the A image (>= M + shift)
@@ -407,6 +484,7 @@ int main() {
   };
   for (int nacc : {1})
   for (const Case &c : cases) {
+    if (c.KB != 4) continue;
     if (c.N > 64) continue;
     g_nacc = nacc;
     printf("nacc=%d ", nacc);
@@ -416,6 +494,11 @@ int main() {
     printf("   -> slope %.2f cyc/MMA, fixed %.0f cyc\n", (double)(c2 - c1) / (256.0 * c.KB),
            (double)c1 - 32.0 * c.KB * (double)(c2 - c1) / (256.0 * c.KB));
   }
+  run_pair<128, 48, 32, 25>("conv4fwd");
+  run_pair<128, 32, 16, 25>("conv1fwd");
+  run_pair<128, 16, 16, 25>("conv1bwd");
+  run_pair<64, 48, 24, 25>("conv7");
+  run_pair<128, 48, 48, 25>("same48");
   run_rate<128, 16, 1, 8, false>("n16");
   run_rate<128, 32, 1, 8, false>("n32");
   run_rate<128, 48, 1, 8, false>("n48");
