@@ -1,0 +1,127 @@
+// Own test of the C++ host mirror (plasticity_b200/cpp): drives the reference's
+// public API shape — Architecture builder, Nnet, ClBuffer, WeightNumber, the
+// JSON weight file — on cuda:0 and checks the known answers the reference's
+// nnet/nnet_test.cc pins (cited per case).  Exit code 0 = all checks passed.
+#include <cmath>
+#include <cstdio>
+#include <set>
+
+#include "nnet/nnet.h"
+
+static int failures = 0;
+#define EXPECT_NEAR(a, b, eps)                                                            \
+  do {                                                                                    \
+    const double a__ = (a), b__ = (b);                                                    \
+    if (!(std::fabs(a__ - b__) <= (eps) * std::max(1.0, std::fabs(b__)))) {               \
+      std::printf("FAIL %s:%d  %s = %.9g, want %.9g\n", __FILE__, __LINE__, #a, a__, b__); \
+      ++failures;                                                                         \
+    }                                                                                     \
+  } while (0)
+#define EXPECT_TRUE(c)                                                    \
+  do {                                                                    \
+    if (!(c)) {                                                           \
+      std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c);            \
+      ++failures;                                                         \
+    }                                                                     \
+  } while (0)
+
+using namespace nnet;
+
+// dense 3->3 + ReLU, nnet_test.cc:17-70
+static void OneLayerRelu() {
+  Architecture model(3);
+  model.AddDenseLayer(3, symbolic::Relu);
+  Nnet net(model, Nnet::NoWeightInit, CrossEntropy);
+  DenseSymbolGenerator s(Dimensions{3, 3});
+  const double w[3][3] = {{0.1, 0.3, 0.4}, {0.2, 0.2, 0.3}, {0.3, 0.7, 0.9}};
+  for (int o = 0; o < 3; ++o) {
+    for (int i = 0; i < 3; ++i) net.GetWeight(1, s.WeightNumber(o, i)) = w[o][i];
+    net.GetWeight(1, s.WeightNumber(o)) = 1;
+  }
+  auto in = net.MakeBuffer({0.1, 0.2, 0.7});
+  auto out = net.Evaluate(in);
+  out->MoveToCpu();
+  EXPECT_TRUE(out->size() == 3);
+  EXPECT_NEAR(out->at(0), 1.35, 1e-3);
+  EXPECT_NEAR(out->at(1), 1.27, 1e-3);
+  EXPECT_NEAR(out->at(2), 1.8, 1e-3);
+}
+
+// 2-2-2 sigmoid MSE, one SGD step at lr 0.5, nnet_test.cc:194-274
+static void MazurStep() {
+  Architecture model(2);
+  model.AddDenseLayer(2, symbolic::Sigmoid);
+  model.AddDenseLayer(2, symbolic::Sigmoid);
+  DenseSymbolGenerator s(Dimensions{2, 2});
+  model.layers[1].W(s.WeightNumber(0, 0)) = 0.15; model.layers[1].W(s.WeightNumber(0, 1)) = 0.2;
+  model.layers[1].W(s.WeightNumber(0)) = 0.35;
+  model.layers[1].W(s.WeightNumber(1, 0)) = 0.25; model.layers[1].W(s.WeightNumber(1, 1)) = 0.3;
+  model.layers[1].W(s.WeightNumber(1)) = 0.35;
+  model.layers[3].W(s.WeightNumber(0, 0)) = 0.4; model.layers[3].W(s.WeightNumber(0, 1)) = 0.45;
+  model.layers[3].W(s.WeightNumber(0)) = 0.6;
+  model.layers[3].W(s.WeightNumber(1, 0)) = 0.5; model.layers[3].W(s.WeightNumber(1, 1)) = 0.55;
+  model.layers[3].W(s.WeightNumber(1)) = 0.6;
+  Nnet net(model, Nnet::NoWeightInit, MeanSquared);
+  auto in = net.MakeBuffer({0.05, 0.10});
+  auto expected = net.MakeBuffer({0.01, 0.99});
+  auto out = net.Evaluate(in);
+  EXPECT_NEAR(net.Error(out, expected), 0.298371109, 1e-5);
+  out->MoveToCpu();
+  EXPECT_NEAR(out->at(0), 0.75136507, 1e-5);
+  EXPECT_NEAR(out->at(1), 0.772928465, 1e-5);
+  net.SetLearningParameters(Nnet::LearningParameters{0.5});
+  net.Train(in, expected);
+  Architecture &m = net.model();
+  EXPECT_NEAR(m.layers[1].W(s.WeightNumber(0, 0)), 0.149780716, 2e-5);
+  EXPECT_NEAR(m.layers[1].W(s.WeightNumber(1, 1)), 0.29950229, 2e-5);
+  EXPECT_NEAR(m.layers[3].W(s.WeightNumber(0, 0)), 0.35891648, 2e-5);
+  EXPECT_NEAR(m.layers[3].W(s.WeightNumber(1, 1)), 0.561370121, 2e-5);
+}
+
+// conv weight layout, nnet_test.cc:486-581
+static void ConvLayout() {
+  ConvSymbolGenerator s(VolumeDimensions{5, 5, 3}, FilterParams{3, 3, 3, 2, 1, 2});
+  EXPECT_TRUE(s.WeightNumber(0, 0, 0, 0) == 0);
+  EXPECT_TRUE(s.WeightNumber(0, 2, 2, 2) == 26);
+  EXPECT_TRUE(s.WeightNumber(0) == 27);
+  EXPECT_TRUE(s.WeightNumber(1, 0, 0, 0) == 28);
+  EXPECT_TRUE(s.WeightNumber(1) == 55);
+}
+
+// JSON round trip, nnet_test.cc:1159-1215; BatchTrain + per-sample loop smoke.
+static void SaveLoadAndBatch() {
+  Architecture model(3);
+  model.AddDenseLayer(9, symbolic::Relu);
+  model.AddConvolutionLayer({3, 3, 1}, {2, 2, 1, 1, 0, 2});
+  model.AddDenseLayer(9, symbolic::Relu);
+  model.AddSoftmaxLayer(9);
+  Nnet a(model, Nnet::Xavier, CrossEntropy, 8);
+  const std::string saved = a.WeightsToString();
+  Nnet b(model, Nnet::NoWeightInit, CrossEntropy, 8);
+  EXPECT_TRUE(b.LoadWeightsFromString(saved));
+  EXPECT_TRUE(b.WeightsToString() == saved);
+  EXPECT_TRUE(!b.LoadWeightsFromString("{\"version\":\"nope\"}"));
+  // the same minibatch step on both copies gives the same weights
+  std::vector<std::unique_ptr<compute::ClBuffer>> ins, outs;
+  for (int k = 0; k < 6; ++k) {
+    ins.push_back(a.MakeBuffer({0.1 * k, -0.2 + 0.05 * k, 0.3}));
+    std::vector<double> e(9, 0.0);
+    e[k % 9] = 1.0;
+    outs.push_back(a.MakeBuffer(e));
+  }
+  a.SetLearningParameters(Nnet::LearningParameters{0.01});
+  b.SetLearningParameters(Nnet::LearningParameters{0.01});
+  a.BatchTrain(ins, outs, std::set<int>{0, 1, 2, 3, 4, 5});
+  b.BatchTrain(ins, outs, std::set<int>{0, 1, 2, 3, 4, 5});
+  EXPECT_TRUE(a.WeightsToString() == b.WeightsToString());
+  EXPECT_TRUE(a.WeightsToString() != saved);
+}
+
+int main() {
+  OneLayerRelu();
+  MazurStep();
+  ConvLayout();
+  SaveLoadAndBatch();
+  std::printf(failures ? "mirror_test: %d FAILED\n" : "mirror_test: all passed\n", failures);
+  return failures ? 1 : 0;
+}
