@@ -336,25 +336,20 @@ def run_ours(args):
     hx, he, ho = C.c_void_p(), C.c_void_p(), C.c_void_p()
     L.call("pb_host_alloc", x.nbytes, C.byref(hx))
     L.call("pb_host_alloc", e.nbytes, C.byref(he))
-    L.call("pb_host_alloc", B * 10 * 4, C.byref(ho))
+    L.call("pb_host_alloc", 2 * B * 10 * 4, C.byref(ho))
     C.memmove(hx, x.ctypes.data, x.nbytes)
     C.memmove(he, e.ctypes.data, e.nbytes)
-    sx, se = C.c_void_p(), C.c_void_p()
-    L.call("pb_buffer_alloc", ctx, B * 3072, C.byref(sx))
-    L.call("pb_buffer_alloc", ctx, B * 10, C.byref(se))
-    last = C.c_void_p()
-    L.call("pb_nnet_layer_output", net.h, net.number_of_layers() - 1, C.byref(last))
 
     def step_e2e(i):
+        # The user-facing call for host-resident data: pinned host inputs in, the
+        # step's network outputs (batch x 10 scores) back to pinned host memory.
+        # Asynchronous: the H2D of step i+1 overlaps the compute of step i (two
+        # device staging slots inside the library); every step still moves its own
+        # inputs and result inside the timed region.
         off = (i % NB) * B
-        L.call("pb_buffer_write_f32_async", ctx, sx, C.c_void_p(hx.value + off * 3072 * 4), B * 3072)
-        L.call("pb_buffer_write_f32_async", ctx, se, C.c_void_p(he.value + off * 10 * 4), B * 10)
-        if comm is None:
-            L.call("pb_nnet_batch_train", net.h, sx, se, B)
-        else:
-            L.call("pb_nnet_batch_train_dp", net.h, comm, sx, se, B)
-        L.call("pb_buffer_read_f32_async", ctx, last, ho, B * 10)
-        L.call("pb_context_finish", ctx)  # the caller holds the result
+        net.BatchTrainHost(C.c_void_p(hx.value + off * 3072 * 4),
+                           C.c_void_p(he.value + off * 10 * 4), B,
+                           C.c_void_p(ho.value + (i % 2) * B * 10 * 4), comm=comm)
 
     for i in range(min(args.warmup, 3)):
         step_e2e(i)

@@ -251,6 +251,17 @@ int pb_comm_allreduce_sum(pb_comm *comm, float *d_buf, int64_t n);
 int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
                            const float *d_expected, int64_t local_batch);
 
+/* The same step fed from HOST memory (pinned: pb_host_alloc), asynchronously:
+ * the inputs of call i+1 are copied to the device by a second stream while call
+ * i computes (two staging slots), and the network outputs of the step (before
+ * the update, batch * num_outputs floats) are copied back to h_outputs
+ * (nullable).  Returns after enqueuing; pb_context_finish() waits for all.  This
+ * is what replaces the per-sample MakeBuffer + MoveToGpu + Train loop of
+ * nnet/cifar_test.cc:423-428 for a host-resident data set.  comm != NULL: the
+ * data-parallel step (pb_nnet_batch_train_dp) on this rank's shard. */
+int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
+                             const float *h_expected, int64_t local_batch, float *h_outputs);
+
 /* ------------------------------------------------------------------------
  * Measurement helpers (bench.py): peak FP32 FFMA throughput and HBM copy
  * bandwidth of this device, measured with CUDA events.

@@ -256,8 +256,11 @@ struct WgGeom {
 };
 
 // One pipeline stage of shared memory: [input tile | ones plane | gradient tile]
-template <int FW, int FH, int TF>
-__global__ void __launch_bounds__(1024, 1)
+// OWC: compile-time output width (0 = runtime): the pixel loop of a row unrolls
+// fully, shared-memory offsets become immediates and the loads of the next
+// 4-pixel step are issued under the FFMAs of the current one.
+template <int FW, int FH, int TF, int OWC, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 conv_wgrad_s1_kernel(const float *__restrict__ In, const float *__restrict__ G,
                      float *__restrict__ partial, const WgGeom g) {
   extern __shared__ __align__(16) float smem[];
@@ -314,11 +317,13 @@ conv_wgrad_s1_kernel(const float *__restrict__ In, const float *__restrict__ G,
       const float *gs = st + g.ones_off + g.oh * g.IWs + 8 + (fg * TF) * out_plane;
       const int row0 = rc * g.rows_per_chunk;
       const int row1 = min(g.oh, row0 + g.rows_per_chunk);
+      const int ow = OWC ? OWC : g.ow;
       for (int oy = row0; oy < row1; ++oy) {
         const float *irow = in_base + oy * g.IWs;
-        const float *grow = gs + oy * g.ow;
+        const float *grow = gs + oy * ow;
         float4 lo = *reinterpret_cast<const float4 *>(irow);
-        for (int ox = 0; ox < g.ow; ox += 4) {
+#pragma unroll
+        for (int ox = 0; ox < ow; ox += 4) {
           const float4 hi = *reinterpret_cast<const float4 *>(irow + ox + 4);
           const float in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
@@ -405,13 +410,13 @@ int reduce_partials_update(pb_context *ctx, const float *partial, int n_partial,
   return 0;
 }
 
-template <int FW, int FH, int TF>
+template <int FW, int FH, int TF, int OWC = 0, int MAXT = 1024>
 static int launch_wgrad(pb_context *ctx, const float *I, const float *Wt, const float *G,
                         float *out, const float *lr, int mode, WgGeom g) {
   g.NFG = (g.F + TF - 1) / TF;
   g.P = g.D * FH + 1;
   // thread budget per f-group
-  const int max_u = (1024 / g.NFG) / 32 * 32;
+  const int max_u = (MAXT / g.NFG) / 32 * 32;
   if (max_u < 32 || g.P > max_u) return -1;
   g.RC = std::max(1, std::min(g.oh, max_u / g.P));
   g.rows_per_chunk = (g.oh + g.RC - 1) / g.RC;
@@ -437,7 +442,7 @@ static int launch_wgrad(pb_context *ctx, const float *I, const float *Wt, const 
   const int grid = (g.batch + g.samples_per_cta - 1) / g.samples_per_cta;
   const int nw = g.F * g.K1;
   if (ensure_workspace(ctx, (size_t)grid * nw)) return 1;
-  auto kern = conv_wgrad_s1_kernel<FW, FH, TF>;
+  auto kern = conv_wgrad_s1_kernel<FW, FH, TF, OWC, MAXT>;
   PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   kern<<<grid, threads, smem, ctx->stream>>>(I, G, ctx->workspace, g);
   PB_LAUNCHED(ctx);
@@ -456,7 +461,18 @@ int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const floa
   g.K1 = fw * fh * g.D + 1;
   g.batch = (int)batch;
   if (g.F > 32) return -1;
-  if (fw == 5 && fh == 5) return launch_wgrad<5, 5, 4>(ctx, I, Wt, G, out, lr, mode, g);
+  if (fw == 5 && fh == 5) {
+    static const int maxt = getenv("PB_WGRAD_T") ? atoi(getenv("PB_WGRAD_T")) : 1024;
+    if (maxt == 512) {
+      if (g.ow == 32) return launch_wgrad<5, 5, 4, 32, 512>(ctx, I, Wt, G, out, lr, mode, g);
+      if (g.ow == 16) return launch_wgrad<5, 5, 4, 16, 512>(ctx, I, Wt, G, out, lr, mode, g);
+      if (g.ow == 8) return launch_wgrad<5, 5, 4, 8, 512>(ctx, I, Wt, G, out, lr, mode, g);
+    }
+    if (g.ow == 32) return launch_wgrad<5, 5, 4, 32>(ctx, I, Wt, G, out, lr, mode, g);
+    if (g.ow == 16) return launch_wgrad<5, 5, 4, 16>(ctx, I, Wt, G, out, lr, mode, g);
+    if (g.ow == 8) return launch_wgrad<5, 5, 4, 8>(ctx, I, Wt, G, out, lr, mode, g);
+    return launch_wgrad<5, 5, 4>(ctx, I, Wt, G, out, lr, mode, g);
+  }
   if (fw == 3 && fh == 3) return launch_wgrad<3, 3, 4>(ctx, I, Wt, G, out, lr, mode, g);
   return -1;
 }

@@ -43,6 +43,15 @@ struct pb_nnet {
   //   run as one kernel (head.cu).
   std::vector<char> block;
   int head = -1;
+  // Host-buffer training (pb_nnet_batch_train_host): two device staging slots
+  // filled by a copy stream while the previous step computes.
+  struct HostPipe {
+    cudaStream_t copy = nullptr;
+    float *x[2] = {nullptr, nullptr}, *e[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    int64_t cap = 0;
+    uint64_t calls = 0;
+  } pipe;
   bool alias_input = false;
   bool fuse = true;
 };
@@ -311,6 +320,14 @@ int pb_nnet_destroy(pb_nnet *net) {
   if (!net) return 0;
   cudaSetDevice(net->ctx->device);
   cudaStreamSynchronize(net->ctx->stream);
+  if (net->pipe.copy) {
+    cudaStreamSynchronize(net->pipe.copy);
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(net->pipe.x[i]); cudaFree(net->pipe.e[i]);
+      cudaEventDestroy(net->pipe.copied[i]); cudaEventDestroy(net->pipe.consumed[i]);
+    }
+    cudaStreamDestroy(net->pipe.copy);
+  }
   if (net->train_exec) cudaGraphExecDestroy(net->train_exec);
   cudaFree(net->weights); cudaFree(net->deltas);
   cudaFree(net->grad_a); cudaFree(net->grad_b);
@@ -551,6 +568,45 @@ int pb_nnet_batch_train(pb_nnet *net, const float *d_ins, const float *d_expecte
                         int64_t batch) {
   if (pb_nnet_batch_gradients(net, d_ins, d_expected, batch)) return 1;
   return pb_nnet_apply_deltas(net);
+}
+
+int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
+                             const float *h_expected, int64_t batch, float *h_outputs) {
+  PB_CHECK(net && h_ins && h_expected, "pb_nnet_batch_train_host: null");
+  PB_CHECK(batch >= 1 && batch <= net->max_batch,
+           "pb_nnet_batch_train_host: batch exceeds the max_batch the network was created with");
+  pb_context *ctx = net->ctx;
+  PB_CUDA(cudaSetDevice(ctx->device));
+  pb_nnet::HostPipe &p = net->pipe;
+  const int64_t nin = net->ni[0], nout = net->no.back();
+  if (!p.copy) {
+    PB_CUDA(cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking));
+    p.cap = net->max_batch;
+    for (int i = 0; i < 2; ++i) {
+      PB_CUDA(cudaMalloc((void **)&p.x[i], sizeof(float) * (size_t)(p.cap * nin)));
+      PB_CUDA(cudaMalloc((void **)&p.e[i], sizeof(float) * (size_t)(p.cap * nout)));
+      PB_CUDA(cudaEventCreateWithFlags(&p.copied[i], cudaEventDisableTiming));
+      PB_CUDA(cudaEventCreateWithFlags(&p.consumed[i], cudaEventDisableTiming));
+    }
+  }
+  const int s = (int)(p.calls & 1);
+  // slot s was last read by the step two calls ago
+  if (p.calls >= 2) PB_CUDA(cudaStreamWaitEvent(p.copy, p.consumed[s], 0));
+  PB_CUDA(cudaMemcpyAsync(p.x[s], h_ins, sizeof(float) * (size_t)(batch * nin),
+                          cudaMemcpyHostToDevice, p.copy));
+  PB_CUDA(cudaMemcpyAsync(p.e[s], h_expected, sizeof(float) * (size_t)(batch * nout),
+                          cudaMemcpyHostToDevice, p.copy));
+  PB_CUDA(cudaEventRecord(p.copied[s], p.copy));
+  PB_CUDA(cudaStreamWaitEvent(ctx->stream, p.copied[s], 0));
+  if (comm ? pb_nnet_batch_train_dp(net, comm, p.x[s], p.e[s], batch)
+           : pb_nnet_batch_train(net, p.x[s], p.e[s], batch))
+    return 1;
+  PB_CUDA(cudaEventRecord(p.consumed[s], ctx->stream));
+  if (h_outputs)
+    PB_CUDA(cudaMemcpyAsync(h_outputs, net->outputs.back(), sizeof(float) * (size_t)(batch * nout),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  p.calls++;
+  return 0;
 }
 
 }  // extern "C"

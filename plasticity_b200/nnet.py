@@ -492,6 +492,15 @@ class Nnet:
                    expected.gpu_buffer(), batch)
         self._dev_dirty = [n > 0 for n in self.nw]
 
+    def BatchTrainHost(self, h_inputs, h_expected, batch: int, h_outputs=None, comm=None) -> None:
+        """BatchTrain fed from pinned HOST memory (raw pointers from pb_host_alloc),
+        asynchronous and double-buffered (pb_nnet_batch_train_host): the H2D copy of
+        the next call overlaps this call's compute; h_outputs (nullable) receives the
+        step's pre-update network outputs.  Finish() waits for everything queued."""
+        self._sync_to_device()
+        L.call("pb_nnet_batch_train_host", self.h, comm, h_inputs, h_expected, batch, h_outputs)
+        self._dev_dirty = [n > 0 for n in self.nw]
+
     def Finish(self) -> None:
         L.call("pb_context_finish", self.ctx)
 

@@ -286,3 +286,50 @@ def test_conv_persistent_pipeline_large_batch(ctx, layer):
                           f"layer {layer} input_delta sample {b}")
     # every sample must have been written (no item skipped by the ring)
     assert np.all(np.abs(O).sum(axis=1) > 0) and np.all(np.abs(DI).sum(axis=1) > 0)
+
+
+def test_batch_train_host_pipeline_matches_device_path(ctx):
+    """pb_nnet_batch_train_host (pinned host inputs, copy stream + two staging slots,
+    asynchronous) must leave exactly the weights the device-buffer BatchTrain leaves,
+    and return each step's pre-update network outputs."""
+    name = "mixed"
+    spec = po.spec_text(name)
+    S = po.RestatedNet(spec)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(77)
+    w0 = util.xavier_like(S, rng)
+    B, steps = 8, 5
+    xs = rng.normal(0, 1, (steps, B, S.n_in)).astype(np.float32)
+    es = rng.uniform(0, 1, (steps, B, S.n_out)).astype(np.float32)
+    nets = []
+    for _ in range(2):
+        net = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=B)
+        net.SetLearningParameters(pb.Nnet.LearningParameters(0.02))
+        util.load_product_weights(net, S, w0)
+        nets.append(net)
+    # device path
+    outs_dev = []
+    for t in range(steps):
+        o = nets[0].Evaluate(nets[0].MakeBuffer(xs[t].reshape(-1).astype(np.float64)), batch=B)
+        o.MoveToCpu()
+        outs_dev.append(o.cpu.copy())
+        nets[0].BatchTrain(nets[0].MakeBuffer(xs[t].reshape(-1).astype(np.float64)),
+                           nets[0].MakeBuffer(es[t].reshape(-1).astype(np.float64)), B)
+    # host path: everything in pinned memory, all steps enqueued back to back
+    hx, he, ho = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    L.call("pb_host_alloc", xs.nbytes, C.byref(hx))
+    L.call("pb_host_alloc", es.nbytes, C.byref(he))
+    L.call("pb_host_alloc", steps * B * S.n_out * 4, C.byref(ho))
+    C.memmove(hx, xs.ctypes.data, xs.nbytes)
+    C.memmove(he, es.ctypes.data, es.nbytes)
+    for t in range(steps):
+        nets[1].BatchTrainHost(C.c_void_p(hx.value + t * B * S.n_in * 4),
+                               C.c_void_p(he.value + t * B * S.n_out * 4), B,
+                               C.c_void_p(ho.value + t * B * S.n_out * 4))
+    nets[1].Finish()
+    got = np.ctypeslib.as_array(C.cast(ho, C.POINTER(C.c_float)), shape=(steps, B * S.n_out)).copy()
+    assert np.array_equal(util.read_product_weights(nets[0], S), util.read_product_weights(nets[1], S))
+    for t in range(steps):
+        np.testing.assert_allclose(got[t], outs_dev[t], rtol=1e-5, atol=1e-7)
+    for p in (hx, he, ho):
+        L.call("pb_host_free", p)
