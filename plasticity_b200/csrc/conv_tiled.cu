@@ -449,6 +449,225 @@ static int launch_wgrad(pb_context *ctx, const float *I, const float *Wt, const 
   return reduce_partials_update(ctx, ctx->workspace, grid, nw, Wt, out, lr, mode);
 }
 
+
+// ---------------------------------------------------------------------------
+// Warp-specialised weight gradient (square "same" stride-1 layers, S = W = H =
+// ow = oh known at compile time).  Same per-thread register tile as
+// conv_wgrad_s1_kernel, different orchestration:
+//   warp 0        producer: cp.async of the next sample's input rows (8 B) and
+//                 gradient planes (16 B) into an NST-stage ring; completion is
+//                 signalled on an mbarrier (cp.async.mbarrier.arrive.noinc);
+//   warps 1..     consumers: (f-group, row-chunk, pair) units laid out densely
+//                 over the consumer threads; wait(full[s]) -> FFMA -> one
+//                 arrive(empty[s]) per warp.
+// There is no CTA-wide barrier inside the sample loop, so warps drift and the
+// FFMA pipe stays fed while the ring refills.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ws_smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void ws_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WS_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WS_DONE;\n\t"
+      "bra WS_WAIT;\n\t"
+      "WS_DONE:\n\t"
+      "}\n" ::"r"(ws_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void ws_cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ws_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ws_cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ws_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ws_cp_async_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ws_smem_u32(bar)) : "memory");
+}
+
+constexpr int kWsMaxStages = 8;
+
+template <int FW, int FH, int TF, int S>
+__global__ void __launch_bounds__(1024, 1)
+conv_wgrad_ws_kernel(const float *__restrict__ In, const float *__restrict__ G,
+                     float *__restrict__ partial, const WgGeom g, const int nstage) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ uint64_t full[kWsMaxStages], empty[kWsMaxStages];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_cons_warps = (blockDim.x >> 5) - 1;
+  const int b_begin = blockIdx.x * g.samples_per_cta;
+  const int b_end = min(g.batch, b_begin + g.samples_per_cta);
+  constexpr int PLANE = S * S;
+
+  // zero every stage's input tile (the halo stays zero), fill the ones planes
+  for (int e = tid; e < nstage * g.stage_elems; e += blockDim.x) {
+    const int o = e % g.stage_elems;
+    smem[e] = (o >= g.ones_off && o < g.ones_off + S * g.IWs + 8) ? 1.0f : 0.0f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < nstage; ++s) {
+      ws_mbar_init(&full[s], 32);
+      ws_mbar_init(&empty[s], n_cons_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  float acc[TF][FW];
+#pragma unroll
+  for (int f = 0; f < TF; ++f)
+#pragma unroll
+    for (int x = 0; x < FW; ++x) acc[f][x] = 0.0f;
+
+  // consumer unit of this thread (valid for warps >= 1)
+  const int u = tid - 32;
+  const int per_fg = g.RC * g.P;
+  const int fg = u >= 0 ? u / per_fg : 0;
+  const int r2 = u >= 0 ? u - fg * per_fg : 0;
+  const int rc = r2 / g.P, pr = r2 - rc * g.P;
+  const bool worker = u >= 0 && fg < g.NFG;
+  const bool bias_pair = pr == g.P - 1;
+  const int z = pr / FH, fy = pr - z * FH;
+
+  if (warp == 0) {
+    // ---- producer ----------------------------------------------------------
+    int it = 0;
+    for (int b = b_begin; b < b_end; ++b, ++it) {
+      const int s = it % nstage, ph = (it / nstage) & 1;
+      ws_mbar_wait(&empty[s], ph ^ 1);
+      float *st = smem + s * g.stage_elems;
+      const float *src = In + (int64_t)b * g.D * PLANE;
+      for (int e = lane; e < g.D * PLANE / 2; e += 32) {   // float2 chunks of the interior
+        const int x2 = e % (S / 2);
+        const int t = e / (S / 2);
+        const int y = t % S, zz = t / S;
+        ws_cp_async8(st + (zz * g.IHs + y + g.p) * g.IWs + 2 * x2 + g.p, src + 2 * e);
+      }
+      float *gs = st + g.ones_off + S * g.IWs + 8;
+      const float *gsrc = G + (int64_t)b * g.F * PLANE;
+      for (int e = lane; e < g.F * PLANE / 4; e += 32) ws_cp_async16(gs + 4 * e, gsrc + 4 * e);
+      ws_cp_async_arrive(&full[s]);
+    }
+  } else {
+    // ---- consumers ---------------------------------------------------------
+    int it = 0;
+    for (int b = b_begin; b < b_end; ++b, ++it) {
+      const int s = it % nstage, ph = (it / nstage) & 1;
+      ws_mbar_wait(&full[s], ph);
+      if (worker) {
+        const float *st = smem + s * g.stage_elems;
+        const float *in_base = bias_pair ? st + g.ones_off : st + (z * g.IHs + fy) * g.IWs;
+        const float *gs = st + g.ones_off + S * g.IWs + 8 + (fg * TF) * PLANE;
+        const int row0 = rc * g.rows_per_chunk;
+        const int row1 = min(S, row0 + g.rows_per_chunk);
+        for (int oy = row0; oy < row1; ++oy) {
+          const float *irow = in_base + oy * g.IWs;
+          const float *grow = gs + oy * S;
+          float4 lo = *reinterpret_cast<const float4 *>(irow);
+#pragma unroll
+          for (int ox = 0; ox < S; ox += 4) {
+            const float4 hi = *reinterpret_cast<const float4 *>(irow + ox + 4);
+            const float in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+            for (int f = 0; f < TF; ++f) {
+              const float4 gv = *reinterpret_cast<const float4 *>(grow + f * PLANE + ox);
+              const float gq[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int x = 0; x < FW; ++x) acc[f][x] = fmaf(gq[q], in[q + x], acc[f][x]);
+            }
+            lo = hi;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ws_mbar_arrive(&empty[s]);
+    }
+  }
+
+  // reduce the row chunks of each (f-group, pair) through shared memory
+  __syncthreads();
+  float *red = smem;  // [NFG][RC][P][TF*FW]
+  if (worker) {
+    float *dst = red + ((fg * g.RC + rc) * g.P + pr) * (TF * FW);
+#pragma unroll
+    for (int f = 0; f < TF; ++f)
+#pragma unroll
+      for (int x = 0; x < FW; ++x) dst[f * FW + x] = acc[f][x];
+  }
+  __syncthreads();
+  float *out = partial + (int64_t)blockIdx.x * g.F * g.K1;
+  for (int e = tid; e < g.NFG * g.P * TF * FW; e += blockDim.x) {
+    const int x = e % FW;
+    int t = e / FW;
+    const int f_in = t % TF; t /= TF;
+    const int pp = t % g.P;
+    const int fgi = t / g.P;
+    const int f = fgi * TF + f_in;
+    if (f >= g.F) continue;
+    float sum = 0.0f;
+    for (int c = 0; c < g.RC; ++c) sum += red[((fgi * g.RC + c) * g.P + pp) * (TF * FW) + f_in * FW + x];
+    if (pp == g.P - 1) {
+      if (x == 0) out[f * g.K1 + g.K1 - 1] = sum;   // bias: every tap saw the same ones
+    } else {
+      const int zz = pp / FH, yy = pp - zz * FH;
+      out[f * g.K1 + (zz * FH + yy) * FW + x] = sum;
+    }
+  }
+}
+
+template <int FW, int FH, int TF, int S>
+static int launch_wgrad_ws(pb_context *ctx, const float *I, const float *Wt, const float *G,
+                           float *out, const float *lr, int mode, WgGeom g) {
+  if (g.W != S || g.H != S || g.ow != S || g.oh != S || (S & 3)) return -1;
+  g.NFG = (g.F + TF - 1) / TF;
+  g.P = g.D * FH + 1;
+  // densest row-chunk split that fits 31 consumer warps
+  const int max_units = 31 * 32;
+  if (g.NFG * g.P > max_units) return -1;
+  g.RC = std::max(1, std::min(S, max_units / (g.NFG * g.P)));
+  g.rows_per_chunk = (S + g.RC - 1) / g.RC;
+  g.RC = (S + g.rows_per_chunk - 1) / g.rows_per_chunk;
+  const int units = g.NFG * g.RC * g.P;
+  const int threads = 32 + ((units + 31) / 32) * 32;
+  g.IHs = S + 2 * g.p;
+  g.IWs = ((S + 4 + 3) / 4) * 4;
+  if (g.IWs < S + 2 * g.p) g.IWs = ((S + 2 * g.p + 3) / 4) * 4;
+  g.in_elems = g.D * g.IHs * g.IWs;
+  g.g_elems = g.NFG * TF * S * S;
+  g.ones_off = g.in_elems;
+  g.stage_elems = ((g.in_elems + S * g.IWs + 8 + g.g_elems + 3) / 4) * 4;
+  if ((g.ones_off + S * g.IWs + 8) % 4 != 0 || (g.p & 1)) return -1;  // cp.async alignment
+  const size_t red_elems = (size_t)g.NFG * g.RC * g.P * TF * FW;
+  const size_t budget = 220 * 1024;
+  int nstage = (int)std::min<size_t>(kWsMaxStages, budget / (sizeof(float) * g.stage_elems));
+  if (nstage < 2) return -1;
+  const size_t smem = sizeof(float) * std::max<size_t>((size_t)nstage * g.stage_elems, red_elems);
+  if (smem > budget) return -1;
+  if (FH - 1 + S - 1 > g.IHs - 1) return -1;
+  const int n_cta = std::min(g.batch, ctx->num_sms);
+  g.samples_per_cta = (g.batch + n_cta - 1) / n_cta;
+  const int grid = (g.batch + g.samples_per_cta - 1) / g.samples_per_cta;
+  const int nw = g.F * g.K1;
+  if (ensure_workspace(ctx, (size_t)grid * nw)) return 1;
+  auto kern = conv_wgrad_ws_kernel<FW, FH, TF, S>;
+  PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+  kern<<<grid, threads, smem, ctx->stream>>>(I, G, ctx->workspace, g, nstage);
+  PB_LAUNCHED(ctx);
+  return reduce_partials_update(ctx, ctx->workspace, grid, nw, Wt, out, lr, mode);
+}
+
 int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const float *I,
                              const float *Wt, const float *G, float *out, const float *lr,
                              int mode, int64_t batch) {
@@ -462,6 +681,14 @@ int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const floa
   g.batch = (int)batch;
   if (g.F > 32) return -1;
   if (fw == 5 && fh == 5) {
+    static const bool use_ws = !(getenv("PB_WGRAD_WS") && getenv("PB_WGRAD_WS")[0] == '0');
+    if (use_ws && g.W == g.ow && g.H == g.oh && g.ow == g.oh) {
+      int rc = -1;
+      if (g.ow == 32) rc = launch_wgrad_ws<5, 5, 4, 32>(ctx, I, Wt, G, out, lr, mode, g);
+      else if (g.ow == 16) rc = launch_wgrad_ws<5, 5, 4, 16>(ctx, I, Wt, G, out, lr, mode, g);
+      else if (g.ow == 8) rc = launch_wgrad_ws<5, 5, 4, 8>(ctx, I, Wt, G, out, lr, mode, g);
+      if (rc >= 0) return rc;
+    }
     static const int maxt = getenv("PB_WGRAD_T") ? atoi(getenv("PB_WGRAD_T")) : 1024;
     if (maxt == 512) {
       if (g.ow == 32) return launch_wgrad<5, 5, 4, 32, 512>(ctx, I, Wt, G, out, lr, mode, g);
