@@ -26,10 +26,11 @@
 // and the epilogue adds the two column groups: fp32-level accuracy (dropped
 // term lo*lo ~ 2^-22), inside the |rel| <= 1e-4 bar.
 //
-// Warp roles (416 threads, one persistent CTA per SM):
-//   warps 0-3  epilogue: tcgen05.ld accumulators -> registers -> bias -> global
-//   warp  4    MMA issuer (one elected lane), TMEM allocator
-//   warps 5-12 producers: global CHW fp32 -> hi/lo split -> shared memory
+// Warp roles (544 threads, one persistent CTA per SM):
+//   warps 0-7  epilogue: tcgen05.ld accumulators -> registers -> bias -> global
+//              (warp w reads TMEM lane quadrant w&3; warps 0-3 / 4-7 split the channels)
+//   warp  8    MMA issuer (one elected lane), TMEM allocator
+//   warps 9-16 producers: global CHW fp32 -> hi/lo split -> shared memory
 // Two shared-memory stages and two TMEM accumulator stages, mbarrier
 // full/empty pairs (tcgen05.commit arrives on the "empty"/"full" barriers).
 // Measured operand-fetch bound of this instruction shape: (M+N)/4 cycles per
@@ -120,6 +121,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -136,9 +147,11 @@ constexpr uint32_t make_idesc(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
-// warps 0-3 epilogue, warp 4 MMA issuer, warps 5-12 producers
+// warps 0-7 epilogue, warp 8 MMA issuer, warps 9-16 producers
+constexpr int kEpilogue = 256;
+constexpr int kMmaWarp = kEpilogue / 32;
 constexpr int kProducers = 256;
-constexpr int kThreads = 160 + kProducers;
+constexpr int kThreads = kEpilogue + 32 + kProducers;
 
 struct KBlock {
   int first, second;  // chunk ids (tap*CH + c); second == -1: zero-weight dummy
@@ -193,6 +206,40 @@ struct UCfg {
     return o1 > o0 ? KBlock{j0, j1, o0, o1 - o0} : KBlock{j1, j0, o1, o0 - o1};
   }
 };
+
+
+// Epilogue of one accumulator tile for one half of the output channels:
+// out = (hi*hi + hi*lo columns) + bias -> global; optionally the 2x2 max-pool of
+// act(out) (act is monotone, so pool(act(x)) == act(pool(x)) exactly: one
+// activation per window instead of four).
+template <class C, int ACT, int HALF>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float *bias_s, float *dst,
+                                              float *dst2, bool row_ok, bool writer) {
+  constexpr int FHALF = (C::OC + 1) / 2;
+  constexpr int F0 = HALF * FHALF;
+  constexpr int NF = (C::OC - F0) < FHALF ? (C::OC - F0) : FHALF;
+  constexpr int C0 = F0 & ~7;                       // 8-aligned first column loaded
+  constexpr int LW = (F0 - C0 + NF <= 8) ? 8 : 16;  // columns per tcgen05.ld
+  static_assert(F0 - C0 + NF <= 16, "channel half must fit one 16-column load");
+  static_assert(C::NP + C0 + LW <= C::N1, "loads stay inside the tile's accumulator columns");
+  if (NF <= 0) return;
+  float vh[LW], vl[LW];
+  if (LW == 8) { tmem_ld8(taddr + C0, vh); tmem_ld8(taddr + C::NP + C0, vl); }
+  else { tmem_ld16(taddr + C0, vh); tmem_ld16(taddr + C::NP + C0, vl); }
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    const int f = F0 + j;
+    const float v = (vh[f - C0] + vl[f - C0]) + bias_s[f];
+    if (row_ok) dst[(int64_t)f * C::H * C::W] = v;
+    if (ACT >= 0) {
+      // 2x2 window partners: x^1 is lane^1, row^1 is lane^8 (row groups of 8 lanes)
+      float m = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+      if (writer) dst2[(int64_t)f * (C::H / 2) * (C::W / 2)] = act_fwd<(ACT >= 0 ? ACT : 0)>(m);
+    }
+  }
+}
 
 // ACT >= 0: fused epilogue — additionally writes Out2 = 2x2 max-pool of
 // act(conv output) (MaxPoolLayer forward of ActivationLayer forward).
@@ -254,10 +301,10 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
     mbar_init(&a_full[0], kProducers); mbar_init(&a_full[1], kProducers);
     mbar_init(&a_empty[0], 1);  mbar_init(&a_empty[1], 1);
     mbar_init(&d_full[0], 1);   mbar_init(&d_full[1], 1);
-    mbar_init(&d_empty[0], 128); mbar_init(&d_empty[1], 128);
+    mbar_init(&d_empty[0], kEpilogue); mbar_init(&d_empty[1], kEpilogue);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_ptr)),
                  "r"(2u * C::TMEM_STAGE)
@@ -271,11 +318,11 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   const uint32_t tmem_base = *tmem_ptr;
   const int n_items = batch * C::IPS;
 
-  if (warp >= 5) {
+  if (warp > kMmaWarp) {
     // ---- producers: global CHW -> [chunk][pixel][4] hi / lo ----------------
     // All global loads of an item are issued before the first conversion so the
     // memory latency is paid once per item, not once per element.
-    const int ptid = tid - 160;
+    const int ptid = tid - (kEpilogue + 32);
     constexpr int TOTAL = C::CH * C::SR * C::W;
     constexpr int ITERS = (TOTAL + kProducers - 1) / kProducers;
     int it = 0;
@@ -319,7 +366,7 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
       fence_async_proxy();
       mbar_arrive(&a_full[s]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ---- MMA issuer ----------------------------------------------------------
     const bool leader = elect_one();
     constexpr uint32_t idesc1 = make_idesc(C::MT, C::N1), idesc2 = make_idesc(C::MT, C::N2);
@@ -368,28 +415,31 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
       tc_fence_after();
       const int b = item / C::IPS, rb = item - b * C::IPS;
       // MT=128: TMEM lane = tile row.  MT=64: row i sits in lane 32*(i/16) + i%16.
-      const int row = C::MT == 128 ? warp * 32 + lane : warp * 16 + lane;
+      const int quad = warp & 3, half = warp >> 2;
+      const int row = C::MT == 128 ? quad * 32 + lane : quad * 16 + lane;
       const bool row_ok = C::MT == 128 || lane < 16;
       const int r = rb * C::RI + (row >> 3), xin = row & 7;
       if (C::NS) {
         // stage Q for the whole item, release TMEM, then gather the fx taps
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous item's gather is done
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous item's gather is done
+        if (half == 0) {
 #pragma unroll 1
-        for (int tile = 0; tile < C::NT; ++tile) {
-          float v[C::N1];
-          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                                 (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
+          for (int tile = 0; tile < C::NT; ++tile) {
+            float v[C::N1];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                   (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
 #pragma unroll
-          for (int q = 0; q < C::N1 / 16; ++q) tmem_ld16(taddr + q * 16, v + q * 16);
-          tmem_ld_wait();
-          float *rec = stg + ((row >> 3) * C::W + tile * 8 + xin) * C::STG_REC;
+            for (int q = 0; q < C::N1 / 16; ++q) tmem_ld16(taddr + q * 16, v + q * 16);
+            tmem_ld_wait();
+            float *rec = stg + ((row >> 3) * C::W + tile * 8 + xin) * C::STG_REC;
 #pragma unroll
-          for (int n = 0; n < C::NOUT; ++n) rec[n] = v[n] + v[C::NP + n];
+            for (int n = 0; n < C::NOUT; ++n) rec[n] = v[n] + v[C::NP + n];
+          }
         }
         tc_fence_before();
         mbar_arrive(&d_empty[s]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int p = tid; p < C::RI * C::W; p += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int p = tid; p < C::RI * C::W; p += kEpilogue) {
           const int rl = p / C::W, c = p - rl * C::W;
           float *dst = Out + (((int64_t)b * C::OC) * C::H + rb * C::RI + rl) * C::W + c;
 #pragma unroll
@@ -405,34 +455,17 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
         }
         continue;
       }
+      const bool writer = row_ok && !(lane & 1) && !(lane & 8);
 #pragma unroll 1
       for (int tile = 0; tile < C::NT; ++tile) {
-        float v[C::N1];
         const uint32_t taddr =
-            tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
-#pragma unroll
-        for (int q = 0; q < C::N1 / 16; ++q) tmem_ld16(taddr + q * 16, v + q * 16);
-        tmem_ld_wait();
-#pragma unroll
-        for (int f = 0; f < C::OC; ++f) v[f] = (v[f] + v[C::NP + f]) + bias_s[f];
-        if (row_ok) {
-          float *dst = Out + (((int64_t)b * C::OC) * C::H + r) * C::W + tile * 8 + xin;
-#pragma unroll
-          for (int f = 0; f < C::OC; ++f) dst[(int64_t)f * C::H * C::W] = v[f];
-        }
-        if (ACT >= 0) {
-          // 2x2 window partners: x^1 is lane^1, row^1 is lane^8 (row groups of 8 lanes)
-          const bool writer = row_ok && !(lane & 1) && !(lane & 8);
-          float *dst2 = Out2 + (((int64_t)b * C::OC) * (C::H / 2) + (r >> 1)) * (C::W / 2) +
-                        ((tile * 8 + xin) >> 1);
-#pragma unroll
-          for (int f = 0; f < C::OC; ++f) {
-            float m = act_fwd<(ACT >= 0 ? ACT : 0)>(v[f]);
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-            if (writer) dst2[(int64_t)f * (C::H / 2) * (C::W / 2)] = m;
-          }
-        }
+            tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
+        float *dst = Out + (((int64_t)b * C::OC) * C::H + r) * C::W + tile * 8 + xin;
+        float *dst2 = ACT >= 0 ? Out2 + (((int64_t)b * C::OC) * (C::H / 2) + (r >> 1)) * (C::W / 2) +
+                                     ((tile * 8 + xin) >> 1)
+                               : nullptr;
+        if (half == 0) epilogue_tile<C, ACT, 0>(taddr, bias_s, dst, dst2, row_ok, writer);
+        else epilogue_tile<C, ACT, 1>(taddr, bias_s, dst, dst2, row_ok, writer);
       }
       tc_fence_before();
       mbar_arrive(&d_empty[s]);
@@ -442,7 +475,7 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   // ---- teardown ------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(2u * C::TMEM_STAGE)
                  : "memory");

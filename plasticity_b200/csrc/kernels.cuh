@@ -93,7 +93,12 @@ __device__ __forceinline__ void apply_update(int mode, float *out, const float *
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float x) {
   if (ACT == PB_RELU) return (x >= 0.0f) ? x : 0.0f;
-  if (ACT == PB_LEAKY_RELU) return (x >= 0.0f) ? x : x / 10.0f;
+  if (ACT == PB_LEAKY_RELU) {
+    // x / 10 as reciprocal multiply + one FMA correction step (the correctly
+    // rounded quotient for normal operands) instead of the generic division.
+    const float q = x * 0.1f;
+    return (x >= 0.0f) ? x : fmaf(fmaf(q, -10.0f, x), 0.1f, q);
+  }
   if (ACT == PB_SIGMOID) return 1.0f / (1.0f + ref_exp(-x));
   return x;
 }
