@@ -162,61 +162,41 @@ def run_reference(args):
     return 0
 
 
-def kernel_table(pb, L, np, net, ctx, stream, torch, batch):
-    """Time every (layer, kernel) of one training step in isolation with CUDA
-    events on the library's stream; returns rows sorted by time."""
-    import ctypes as C
-    model = net.model_
-    rows = []
-    lr = C.c_void_p()
-    L.call("pb_buffer_alloc", ctx, 1, C.byref(lr))
-    L.call("pb_buffer_fill", ctx, lr, 1e-4, 1)
+def step_profile(L, net, xi, ei, batch, reps=5):
+    """Per-kernel-group times of the step as it really runs (fused plan), from CUDA
+    events recorded inside the library (pb_nnet_profile_step); averaged over reps."""
+    buf = C.create_string_buffer(1 << 16)
+    acc, order = {}, []
+    for _ in range(reps + 1):
+        L.call("pb_nnet_profile_step", net.h, xi, ei, batch, buf, len(buf))
+        rows = [l.split("\t") for l in buf.value.decode().strip().split("\n") if l]
+        if _ == 0:
+            continue  # warm
+        for label, ms in rows:
+            if label not in acc:
+                acc[label] = 0.0
+                order.append(label)
+            acc[label] += float(ms) / reps
+    return [(k, acc[k]) for k in order]
 
-    def dev(n, val=None):
-        p = C.c_void_p()
-        L.call("pb_buffer_alloc", ctx, n, C.byref(p))
-        L.call("pb_buffer_fill", ctx, p, 0.01 if val is None else val, n)
-        return p
 
-    def timeit(fn, reps=5):
-        fn()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            fn()
-        e1.record(stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1) / reps
-
-    for i, layer in enumerate(model.layers):
-        d = layer.desc
-        ni, no, nw = layer.num_inputs, layer.num_outputs, layer.weights.size
-        I, O, G, dI = dev(ni * batch), dev(no * batch), dev(no * batch), dev(ni * batch)
-        W = dev(nw) if nw else None
-        out = dev(nw) if nw else None
-        macs = 0
-        if d.kind == L.PB_CONVOLUTION:
-            macs = no * d.filter_width * d.filter_height * d.filter_depth
-        elif d.kind == L.PB_DENSE:
-            macs = ni * no
-        t = timeit(lambda: L.call("pb_layer_evaluate", ctx, C.byref(d), I, W, O, batch))
-        rows.append({"layer": layer.LayerSuffix(), "kernel": "evaluate", "ms": t,
-                     "flop": 2.0 * macs * batch, "bytes": 4.0 * (ni + no) * batch})
-        t = timeit(lambda: L.call("pb_layer_input_delta", ctx, C.byref(d), I, W, G, dI, batch))
-        rows.append({"layer": layer.LayerSuffix(), "kernel": "input_delta", "ms": t,
-                     "flop": 2.0 * macs * batch, "bytes": 4.0 * (ni + no) * batch})
-        if nw:
-            t = timeit(lambda: L.call("pb_layer_weight_update", ctx, C.byref(d), I, W, G, out, lr,
-                                      L.PB_WEIGHT_DELTAS, batch))
-            rows.append({"layer": layer.LayerSuffix(), "kernel": "weight_update", "ms": t,
-                         "flop": 2.0 * macs * batch, "bytes": 4.0 * (ni + no) * batch})
-        for p in (I, O, G, dI, W, out):
-            if p is not None:
-                L.call("pb_buffer_free", ctx, p)
-    L.call("pb_buffer_free", ctx, lr)
-    rows.sort(key=lambda r: -r["ms"])
-    return rows
+def layer_flop(net, L, label, batch):
+    """Algorithmic FLOPs (2 x MAC) of one kernel group, from the layer descriptor."""
+    import re
+    m = re.match(r"(?:convolution|dense)_layer_(\d+)", label)
+    if not m or label.startswith("dense_layer") and ".." in label:
+        idx = re.match(r"dense_layer_(\d+)\.\.", label)
+        if not idx:
+            return 0.0
+        l = net.model_.layers[int(idx.group(1))]
+        return 2.0 * 2 * l.num_inputs * l.num_outputs * batch  # forward + input gradient
+    l = net.model_.layers[int(m.group(1))]
+    d = l.desc
+    if d.kind == L.PB_CONVOLUTION:
+        macs = l.num_outputs * d.filter_width * d.filter_height * d.filter_depth
+    else:
+        macs = l.num_inputs * l.num_outputs
+    return 2.0 * macs * batch
 
 
 def run_ours(args):
@@ -371,33 +351,56 @@ def run_ours(args):
     if rank == 0:
         tf = C.c_double()
         L.call("pb_measure_fp32_tflops", ctx, C.byref(tf))
-        rows = kernel_table(pb, L, np, net, ctx, stream, torch, B)
+        xi0, ei0 = C.c_void_p(px.value), C.c_void_p(pe.value)
+        prof = step_profile(L, net, xi0, ei0, B)
+        rows = [{"kernel": k, "ms": ms, "flop": layer_flop(net, L, k, B)} for k, ms in prof]
+        rows.sort(key=lambda r: -r["ms"])
         step_ms = ms / args.steps
-        total_iso = sum(r["ms"] for r in rows)
-        top = rows[0]
+        total_prof = sum(r["ms"] for r in rows)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        if top["flop"] > 0:
-            roof = {"bound": "fp32", "kernel": f'{top["layer"]}:{top["kernel"]}',
-                    "achieved": top["flop"] / (top["ms"] * 1e-3) / 1e12, "peak": tf.value,
-                    "unit": "TFLOP/s", "traffic": None,
-                    "peak_source": "FFMA micro-benchmark in this run (pb_measure_fp32_tflops); "
-                                   f"nominal {NOMINAL_FP32_TFLOPS:.1f}; MEASURED_PEAKS.json has "
-                                   "no FP32 entry",
-                    "share_of_step": top["ms"] / total_iso}
-        else:
-            roof = {"bound": "hbm", "kernel": f'{top["layer"]}:{top["kernel"]}',
-                    "achieved": top["bytes"] / (top["ms"] * 1e-3) / 1e9, "peak": hbm_peak,
-                    "unit": "GB/s", "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                    "share_of_step": top["ms"] / total_iso}
-        roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
-        whole = {"achieved_tflops": TRAIN_FLOP_PER_SAMPLE * B / (step_ms * 1e-3) / 1e12 if world == 1
-                 else TRAIN_FLOP_PER_SAMPLE * B * world / (step_ms * 1e-3) / 1e12,
+        bf16_peak = peaks.get("bf16_tflops", 1590.0)
+        top = rows[0]
+
+        def roofline_of(r):
+            tensor = "tcgen05" in r["kernel"] or (r["kernel"].startswith("convolution") and
+                                                  r["kernel"].endswith(":input_delta"))
+            if r["flop"] > 0 and not tensor:
+                out = {"bound": "fp32", "peak": tf.value, "unit": "TFLOP/s",
+                       "peak_source": "FP32 FFMA micro-benchmark in this run (pb_measure_fp32_tflops; "
+                                      f"nominal {NOMINAL_FP32_TFLOPS:.1f}); MEASURED_PEAKS.json has no "
+                                      "FP32 entry. The weight gradient has no tensor-core form at these "
+                                      "shapes (DESIGN.md section 3)"}
+            elif r["flop"] > 0:
+                out = {"bound": "tensor", "peak": bf16_peak, "unit": "TFLOP/s",
+                       "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else
+                                       "fallback 1590") + "; the kernel is 3xTF32 (TF32 dense peak is "
+                                       "half the bf16 figure, and every product costs 2 MMA passes), "
+                                       "bounded by shared-memory operand fetch at N<=48"}
+            else:
+                out = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
+                       "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
+            out["kernel"] = r["kernel"]
+            out["achieved"] = r["flop"] / (r["ms"] * 1e-3) / 1e12 if r["flop"] > 0 else None
+            out["frac"] = out["achieved"] / out["peak"] if out["achieved"] else None
+            out["ms"] = r["ms"]
+            out["share_of_step"] = r["ms"] / total_prof
+            out["traffic"] = traffic.get(r["kernel"])
+            return out
+
+        roof = roofline_of(top)
+        top_tc = next((r for r in rows if "tcgen05" in r["kernel"]), None)
+        roof_tensor = roofline_of(top_tc) if top_tc else None
+        whole = {"achieved_tflops": TRAIN_FLOP_PER_SAMPLE * B * world / (step_ms * 1e-3) / 1e12,
                  "fp32_peak_tflops_measured": tf.value * world,
                  "flop_per_sample": TRAIN_FLOP_PER_SAMPLE}
         whole["frac"] = whole["achieved_tflops"] / whole["fp32_peak_tflops_measured"]
@@ -423,10 +426,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * 10 * 4},
             "gpu_launches": n_launch,
             "roofline": roof,
+            "roofline_tensor": roof_tensor,
             "whole_step": whole,
             "cpu_baseline": cpu,
-            "top_kernels": [{"k": f'{r["layer"]}:{r["kernel"]}', "ms": round(r["ms"], 4)}
-                            for r in rows[:6]],
+            "step_kernels": [{"k": r["kernel"], "ms": round(r["ms"], 4)} for r in rows],
         }
         if args.table:
             with open(args.table, "w") as f:

@@ -262,6 +262,12 @@ int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
 int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
                              const float *h_expected, int64_t local_batch, float *h_outputs);
 
+/* One pb_nnet_batch_train step with a CUDA event after every kernel group; writes
+ * "label<TAB>milliseconds<NL>" lines (the kernels the step really runs: fused
+ * convolution blocks, the fused head, ...) into `out`.  Measurement only. */
+int pb_nnet_profile_step(pb_nnet *net, const float *d_ins, const float *d_expected,
+                         int64_t batch, char *out, size_t cap);
+
 /* ------------------------------------------------------------------------
  * Measurement helpers (bench.py): peak FP32 FFMA throughput and HBM copy
  * bandwidth of this device, measured with CUDA events.

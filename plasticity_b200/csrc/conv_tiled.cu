@@ -497,8 +497,8 @@ __device__ __forceinline__ void ws_cp_async_arrive(uint64_t *bar) {
 
 constexpr int kWsMaxStages = 8;
 
-template <int FW, int FH, int TF, int S>
-__global__ void __launch_bounds__(1024, 1)
+template <int FW, int FH, int TF, int S, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 conv_wgrad_ws_kernel(const float *__restrict__ In, const float *__restrict__ G,
                      float *__restrict__ partial, const WgGeom g, const int nstage) {
   extern __shared__ __align__(16) float smem[];
@@ -627,14 +627,16 @@ conv_wgrad_ws_kernel(const float *__restrict__ In, const float *__restrict__ G,
   }
 }
 
-template <int FW, int FH, int TF, int S>
+// MAXT bounds the block size so ptxas may use 65536/MAXT registers per thread
+// (the accumulator tile spills at the 64 registers a 1024-thread block allows).
+template <int FW, int FH, int TF, int S, int MAXT>
 static int launch_wgrad_ws(pb_context *ctx, const float *I, const float *Wt, const float *G,
                            float *out, const float *lr, int mode, WgGeom g) {
   if (g.W != S || g.H != S || g.ow != S || g.oh != S || (S & 3)) return -1;
   g.NFG = (g.F + TF - 1) / TF;
   g.P = g.D * FH + 1;
   // densest row-chunk split that fits 31 consumer warps
-  const int max_units = 31 * 32;
+  const int max_units = MAXT - 32;
   if (g.NFG * g.P > max_units) return -1;
   g.RC = std::max(1, std::min(S, max_units / (g.NFG * g.P)));
   g.rows_per_chunk = (S + g.RC - 1) / g.RC;
@@ -661,7 +663,7 @@ static int launch_wgrad_ws(pb_context *ctx, const float *I, const float *Wt, con
   const int grid = (g.batch + g.samples_per_cta - 1) / g.samples_per_cta;
   const int nw = g.F * g.K1;
   if (ensure_workspace(ctx, (size_t)grid * nw)) return 1;
-  auto kern = conv_wgrad_ws_kernel<FW, FH, TF, S>;
+  auto kern = conv_wgrad_ws_kernel<FW, FH, TF, S, MAXT>;
   PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
   kern<<<grid, threads, smem, ctx->stream>>>(I, G, ctx->workspace, g, nstage);
   PB_LAUNCHED(ctx);
@@ -684,9 +686,14 @@ int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const floa
     static const bool use_ws = !(getenv("PB_WGRAD_WS") && getenv("PB_WGRAD_WS")[0] == '0');
     if (use_ws && g.W == g.ow && g.H == g.oh && g.ow == g.oh) {
       int rc = -1;
-      if (g.ow == 32) rc = launch_wgrad_ws<5, 5, 4, 32>(ctx, I, Wt, G, out, lr, mode, g);
-      else if (g.ow == 16) rc = launch_wgrad_ws<5, 5, 4, 16>(ctx, I, Wt, G, out, lr, mode, g);
-      else if (g.ow == 8) rc = launch_wgrad_ws<5, 5, 4, 8>(ctx, I, Wt, G, out, lr, mode, g);
+      if (g.ow == 32) rc = launch_wgrad_ws<5, 5, 4, 32, 768>(ctx, I, Wt, G, out, lr, mode, g);
+      else if (g.ow == 16) rc = launch_wgrad_ws<5, 5, 4, 16, 896>(ctx, I, Wt, G, out, lr, mode, g);
+      else if (g.ow == 8) rc = launch_wgrad_ws<5, 5, 4, 8, 576>(ctx, I, Wt, G, out, lr, mode, g);
+      if (rc < 0) {  // shape does not fit the tuned block size: generic budget
+        if (g.ow == 32) rc = launch_wgrad_ws<5, 5, 4, 32, 1024>(ctx, I, Wt, G, out, lr, mode, g);
+        else if (g.ow == 16) rc = launch_wgrad_ws<5, 5, 4, 16, 1024>(ctx, I, Wt, G, out, lr, mode, g);
+        else if (g.ow == 8) rc = launch_wgrad_ws<5, 5, 4, 8, 1024>(ctx, I, Wt, G, out, lr, mode, g);
+      }
       if (rc >= 0) return rc;
     }
     static const int maxt = getenv("PB_WGRAD_T") ? atoi(getenv("PB_WGRAD_T")) : 1024;

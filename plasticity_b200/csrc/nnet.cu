@@ -10,6 +10,10 @@
 // buffers (backprop_gradients_ / next_backprop_gradients_) and a 1-element
 // learning-rate buffer (learning_rate_buffer_).
 #include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -43,6 +47,9 @@ struct pb_nnet {
   //   run as one kernel (head.cu).
   std::vector<char> block;
   int head = -1;
+  // pb_nnet_profile_step: CUDA events recorded after each kernel group of a step
+  bool profiling = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
   // Host-buffer training (pb_nnet_batch_train_host): two device staging slots
   // filled by a copy stream while the previous step computes.
   struct HostPipe {
@@ -91,6 +98,20 @@ __global__ void fetch_sample_kernel(const pb_nnet::Cursor *__restrict__ cur,
 
 __global__ void advance_cursor_kernel(pb_nnet::Cursor *cur) { cur->idx += 1; }
 
+static void mark(pb_nnet *net, const std::string &label) {
+  if (!net->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, net->ctx->stream);
+  net->marks.emplace_back(label, e);
+}
+
+static std::string layer_tag(const pb_nnet *net, int l) {
+  static const char *names[] = {"activation_layer", "dense_layer", "convolution_layer",
+                                "max_pool_layer", "softmax_layer"};
+  return std::string(names[net->layers[l].kind]) + "_" + std::to_string(l);
+}
+
 // Batched forward of the gradient pass with the fused plan.  layer_in[l] is
 // what layer l read (outputs of skipped layers are not materialised).
 static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
@@ -112,6 +133,7 @@ static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
                                                  net->outputs[l + 2], batch);
       if (rc > 0) return 1;
       if (rc == 0) {
+        mark(net, layer_tag(net, l) + ":evaluate+activation+pool (tcgen05)");
         fused_fwd[l] = 1;
         layer_in[l + 1] = net->outputs[l];
         layer_in[l + 2] = nullptr;  // activation output not materialised
@@ -121,6 +143,7 @@ static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
       }
     }
     if (pb_layer_evaluate(net->ctx, &net->layers[l], cur, W, net->outputs[l], batch)) return 1;
+    mark(net, layer_tag(net, l) + ":evaluate");
     cur = net->outputs[l];
   }
   return 0;
@@ -140,6 +163,7 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
                                           net->outputs[l - 2], g, ng, batch);
       if (rc > 0) return 1;
       if (rc == 0) {
+        mark(net, layer_tag(net, l) + "+" + layer_tag(net, l - 1) + ":input_delta");
         float *t = g; g = ng; ng = t;
         l -= 1;  // the activation layer is done too
         continue;
@@ -154,11 +178,13 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
     const float *in = layer_in[l] ? layer_in[l] : net->outputs[l - 1];
     float *W = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
     if (pb_layer_input_delta(net->ctx, L, in, W, g, ng, batch)) return 1;
+    mark(net, layer_tag(net, l) + ":input_delta");
     if (net->nw[l] > 0) {
       const int m = first_chunk ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
       if (pb_layer_weight_update(net->ctx, L, in, W, g, net->deltas + net->w_off[l], net->lr, m,
                                  batch))
         return 1;
+      mark(net, layer_tag(net, l) + ":weight_update");
     }
     float *t = g; g = ng; ng = t;
   }
@@ -524,10 +550,13 @@ int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_exp
             net->outputs[h + 2], ng, g, nb);
         if (rc > 0) return 1;
         if (rc == 0) {
+          pb::mark(net, pb::layer_tag(net, h) + ".." + pb::layer_tag(net, n - 1) +
+                            ":evaluate+error_gradients+input_delta (head)");
           const int m = b0 == 0 ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
           if (pb_layer_weight_update(ctx, &net->layers[h], X, W, ng, net->deltas + net->w_off[h],
                                      net->lr, m, nb))
             return 1;
+          pb::mark(net, pb::layer_tag(net, h) + ":weight_update");
           top = h - 1;
           head_done = true;
         } else {
@@ -561,7 +590,35 @@ int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_exp
 
 int pb_nnet_apply_deltas(pb_nnet *net) {
   PB_CHECK(net, "pb_nnet_apply_deltas: null");
-  return pb_vector_accumulate(net->ctx, net->weights, net->deltas, net->total_w);
+  if (pb_vector_accumulate(net->ctx, net->weights, net->deltas, net->total_w)) return 1;
+  pb::mark(net, "vector_accumulate");
+  return 0;
+}
+
+int pb_nnet_profile_step(pb_nnet *net, const float *d_ins, const float *d_expected, int64_t batch,
+                         char *out, size_t cap) {
+  PB_CHECK(net && out && cap > 2, "pb_nnet_profile_step: null");
+  for (auto &m : net->marks) cudaEventDestroy(m.second);
+  net->marks.clear();
+  net->profiling = true;
+  pb::mark(net, "start");
+  const int rc = pb_nnet_batch_train(net, d_ins, d_expected, batch);
+  net->profiling = false;
+  if (rc) return 1;
+  PB_CUDA(cudaStreamSynchronize(net->ctx->stream));
+  std::string text;
+  for (size_t i = 1; i < net->marks.size(); ++i) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, net->marks[i - 1].second, net->marks[i].second);
+    char buf[64];
+    snprintf(buf, sizeof(buf), "\t%.6f\n", ms);
+    text += net->marks[i].first + buf;
+  }
+  for (auto &m : net->marks) cudaEventDestroy(m.second);
+  net->marks.clear();
+  PB_CHECK(text.size() + 1 <= cap, "pb_nnet_profile_step: output buffer too small");
+  memcpy(out, text.c_str(), text.size() + 1);
+  return 0;
 }
 
 int pb_nnet_batch_train(pb_nnet *net, const float *d_ins, const float *d_expected,

@@ -73,6 +73,39 @@ def main():
             w.writerow([f"{c} [{units[idx[c]]}]" if units[idx[c]] else c for c in cols])
             for d in data:
                 w.writerow([d[idx[c]] for c in cols])
+    # dram traffic per launch of the step's kernels (CIFAR net) -> profiles/traffic.json,
+    # read by bench.py for roofline.traffic
+    full = os.path.join(P, f"{tag}_ncu_full.csv")
+    if os.path.exists(full):
+        import json
+        import re
+        rows = list(csv.DictReader(open(full)))
+        label_of = [
+            (r"conv_wgrad_ws_kernel<5, 5, 4, 32", "convolution_layer_1:weight_update"),
+            (r"conv_wgrad_ws_kernel<5, 5, 4, 16", "convolution_layer_4:weight_update"),
+            (r"conv_wgrad_ws_kernel<5, 5, 4, 8", "convolution_layer_7:weight_update"),
+            (r"UCfg<3, 16, 32, 32, 5, 0, 0>, 2>", "convolution_layer_1:evaluate+activation+pool (tcgen05)"),
+            (r"UCfg<16, 20, 16, 16, 5, 0, 0>, 2>", "convolution_layer_4:evaluate+activation+pool (tcgen05)"),
+            (r"UCfg<20, 20, 8, 8, 5, 0, 0>, 2>", "convolution_layer_7:evaluate+activation+pool (tcgen05)"),
+            (r"UCfg<16, 3, 32, 32, 5, 1, 1>", "convolution_layer_1:input_delta"),
+            (r"UCfg<20, 16, 16, 16, 5, 1, 0>", "convolution_layer_4:input_delta"),
+            (r"UCfg<20, 20, 8, 8, 5, 1, 0>", "convolution_layer_7:input_delta"),
+        ]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = {}
+        for r in rows:
+            name = r["Kernel Name"]
+            total = 0.0
+            for col, v in r.items():
+                m = re.match(r"dram__bytes_(read|write)\.sum \[(\w+)\]", col)
+                if m and v:
+                    total += float(v.replace(",", "")) * unit.get(m.group(2), 1.0)
+            for pat, label in label_of:
+                if pat in name:
+                    traffic[label] = total
+        if traffic:
+            traffic["_source"] = f"ncu --set full capture {tag} (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+            json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     for name in (f"bench_{tag}.json", f"table_{tag}.json"):
         src = os.path.join(G, name)
         if os.path.exists(src):
