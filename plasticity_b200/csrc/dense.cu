@@ -200,6 +200,8 @@ int dense_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, cons
                                             (int64_t)ctx->num_sms * 8);
     dense_fwd_gemv_kernel<<<grid, T, 0, ctx->stream>>>(I, W, O, (int)in, (int)out, batch);
   } else {
+    const int rc = dense_evaluate_umma(ctx, l, I, W, O, batch);
+    if (rc >= 0) return rc;
     dim3 grid(pb_div_up(out, GBN), pb_div_up(batch, GBM));
     gemm_kernel<<<grid, 256, 0, ctx->stream>>>((int)batch, (int)out, (int)in, FwdA{I, in},
                                                FwdB{W, in + 1},
@@ -217,6 +219,8 @@ int dense_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *W,
     dense_bwd_gemv_kernel<<<pb_ew_grid(ctx, batch * in, 128), 128, 0, ctx->stream>>>(
         W, G, dI, (int)in, (int)out, batch);
   } else {
+    const int rc = dense_input_delta_umma(ctx, l, W, G, dI, batch);
+    if (rc >= 0) return rc;
     dim3 grid(pb_div_up(in, GBN), pb_div_up(batch, GBM));
     gemm_kernel<<<grid, 256, 0, ctx->stream>>>((int)batch, (int)in, (int)out, BwdA{G, out},
                                                BwdB{W, in + 1}, BwdEpi{dI, in});
@@ -239,6 +243,8 @@ int dense_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
     dense_wupd_small_kernel<<<pb_ew_grid(ctx, nw, 256), 256, 0, ctx->stream>>>(
         I, W, G, out, lr, (int)in, (int)nout, batch, mode);
   } else {
+    const int rc = dense_weight_update_umma(ctx, l, I, W, G, out, lr, mode, batch);
+    if (rc >= 0) return rc;
     dim3 grid(pb_div_up(in + 1, GBN), pb_div_up(nout, GBM));
     gemm_kernel<<<grid, 256, 0, ctx->stream>>>((int)nout, (int)(in + 1), (int)batch,
                                                WgA{G, nout}, WgB{I, in},

@@ -30,6 +30,16 @@ int dense_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
                         const float *W, const float *G, float *out, const float *lr,
                         int mode, int64_t batch);
 
+// dense_umma.cu: 3xTF32 tcgen05 GEMM for large batched dense products; -1 when
+// the product is too small to be worth a tensor-core launch (or PB_DISABLE_UMMA=1).
+int dense_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
+                        float *O, int64_t batch);
+int dense_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, const float *W, const float *G,
+                           float *dI, int64_t batch);
+int dense_weight_update_umma(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                             const float *W, const float *G, float *out, const float *lr,
+                             int mode, int64_t batch);
+
 // head.cu: fused dense -> activation -> softmax -> error-gradient head (forward and
 // backward in one launch) and the skinny dense weight gradient; -1 outside the envelope.
 int head_forward_backward(pb_context *ctx, const pb_layer_desc *dense, int act, int64_t softmax_n,
