@@ -19,6 +19,9 @@ struct pb_context {
   // Partial-sum workspace for batched weight gradients.
   float *workspace = nullptr;
   size_t workspace_elems = 0;
+  // Re-tiled convolution weights of the implicit-GEMM kernel (conv_gemm_umma.cu).
+  float *aux = nullptr;
+  size_t aux_elems = 0;
 };
 
 namespace pb {
@@ -27,6 +30,7 @@ void set_error(const std::string &msg);
 int fail(const std::string &msg);
 int ensure_stage(pb_context *ctx, size_t elems);
 int ensure_workspace(pb_context *ctx, size_t elems);
+int ensure_aux(pb_context *ctx, size_t elems);
 
 // The reference prints NumericValue::e with 6 significant digits
 // (symbolic/numeric_value.cc:41-53), so its kernels compute pow(2.71828, x).

@@ -40,6 +40,18 @@ int ensure_workspace(pb_context *ctx, size_t elems) {
   return 0;
 }
 
+int ensure_aux(pb_context *ctx, size_t elems) {
+  if (ctx->aux_elems >= elems) return 0;
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->aux) PB_CUDA(cudaFree(ctx->aux));
+  ctx->aux = nullptr;
+  ctx->aux_elems = 0;
+  size_t want = std::max<size_t>(elems, 1 << 20);
+  PB_CUDA(cudaMalloc(&ctx->aux, want * sizeof(float)));
+  ctx->aux_elems = want;
+  return 0;
+}
+
 __global__ void f64_to_f32_kernel(const double *__restrict__ src,
                                   float *__restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -104,6 +116,7 @@ int pb_context_destroy(pb_context *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->aux) cudaFree(ctx->aux);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;

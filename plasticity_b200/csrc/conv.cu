@@ -205,6 +205,8 @@ int conv_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, const
   if (batch >= kTiledMinBatch) {
     int rc = conv_evaluate_umma(ctx, l, I, W, O, batch);
     if (rc >= 0) return rc;
+    rc = conv_evaluate_gemm_umma(ctx, l, I, W, O, nullptr, PB_IDENTITY, batch);
+    if (rc >= 0) return rc;
     rc = conv_evaluate_tiled(ctx, l, I, W, O, batch);
     if (rc >= 0) return rc;
   }

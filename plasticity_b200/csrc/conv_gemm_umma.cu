@@ -1,0 +1,182 @@
+// General 3xTF32 tcgen05 implicit-GEMM convolution, forward
+// (nnet/convolution_layer.cc:36-96), for the large batched shapes of the YOLOv1
+// network (nnet/yolov1.cc:7-231: 7x7/2, 3x3, 1x1, 3x3/2 filters, 3..1024
+// channels) — any filter size, stride and padding:
+//
+//   Out[b,oc,r,c] = bias_oc + sum_{ic,fy,fx} Wk[oc,ic,fy,fx] * In0[b,ic,r*s-p+fy,c*s-p+fx]
+//
+// GEMM view on the skeleton of umma_gemm.cuh: M = (sample, output pixel), N = output
+// channel, K = (tap, input channel) with the channel running fastest.  Activations
+// stay in the reference's planar CHW layout: for a fixed k the 128 pixels of an M
+// tile are (mostly) consecutive addresses, so the A producer is a gather with lanes
+// along the pixels and a pointer that walks the channel planes — the im2col matrix
+// never exists.  Zero padding is a predicate on the tap.  The filters are re-tiled
+// once per call into [oc][tap][ic] (K-major, rows padded to the K stage) by a small
+// pre-pass, so the B producer is the plain aligned float4 path.  The epilogue adds the
+// bias and writes [b][oc][pixel] — lanes along the pixels, coalesced — and can apply
+// the following ActivationLayer in the same pass (second output).
+#include "umma_gemm.cuh"
+
+namespace pb {
+namespace {
+
+using namespace ugemm;
+
+struct ConvArgs : GemmCore {
+  const float *In;    // [batch][C][H][W]
+  const float *Wk;    // re-tiled filters [OC][Kp], k' = tap*ICP + ic
+  const float *Wref;  // reference layout [OC][C*FH*FW + 1] (for the bias)
+  float *Out;         // [batch][OC][OH][OW]
+  float *Out2;        // act(Out), nullable
+  int act;
+  int C, H, W, OC, OH, OW, FH, FW, stride, pad;
+  int ICP;            // channels per tap in K order: 4, 8 or a multiple of 16
+  int taps, Kp;
+  int64_t kref;       // C*FH*FW
+};
+
+// Wk[oc][tap*ICP + ic] = Wref[oc][ic][tap], zero in the padding.
+__global__ void retile_filters_kernel(const float *__restrict__ Wref, float *__restrict__ Wk,
+                                      int OC, int C, int taps, int ICP, int Kp) {
+  const int64_t total = (int64_t)OC * Kp;
+  const int64_t kref1 = (int64_t)C * taps + 1;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t oc = t / Kp;
+    const int k = (int)(t - oc * Kp);
+    const int tap = k / ICP, ic = k - tap * ICP;
+    Wk[t] = (tap < taps && ic < C) ? Wref[oc * kref1 + (int64_t)ic * taps + tap] : 0.0f;
+  }
+}
+
+struct ConvPolicy {
+  using Args = ConvArgs;
+
+  // One output pixel per thread (lanes along M), 16 k values of the stage each.
+  struct A {
+    float v[16];
+    int64_t base_off;  // element offset of (sample, channel 0, iy0, ix0); may point before the plane
+    int iy0, ix0;
+    bool m_ok;
+    __device__ __forceinline__ void init(const Args &) {}
+    __device__ __forceinline__ void tile(const Args &g, int tm, int p) {
+      const int m = tm * BM + p;
+      m_ok = m < g.M;
+      const int mm = m_ok ? m : 0;
+      const int ohw = g.OH * g.OW;
+      const int b = mm / ohw, pix = mm - b * ohw;
+      const int r = pix / g.OW, c = pix - r * g.OW;
+      iy0 = r * g.stride - g.pad;
+      ix0 = c * g.stride - g.pad;
+      base_off = (int64_t)b * g.C * g.H * g.W + (int64_t)iy0 * g.W + ix0;
+    }
+    __device__ __forceinline__ void load(const Args &g, int ks, int) {
+      const int64_t hw = (int64_t)g.H * g.W;
+      if (g.ICP >= 16) {
+        // one tap per stage, 16 consecutive channels
+        const int per = g.ICP >> 4;
+        const int tap = ks / per, icb = ks - tap * per;
+        const int fy = tap / g.FW, fx = tap - fy * g.FW;
+        const bool ok = m_ok && tap < g.taps && (unsigned)(iy0 + fy) < (unsigned)g.H &&
+                        (unsigned)(ix0 + fx) < (unsigned)g.W;
+        const float *q = g.In + base_off + (int64_t)(icb * 16) * hw + fy * g.W + fx;
+        if (ok) {
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk, q += hw) v[kk] = __ldg(q);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) v[kk] = 0.0f;
+        }
+      } else {
+        // few input channels (the RGB layer): 16 / ICP taps per stage
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int kq = ks * 16 + 4 * c;
+          const int tap = kq / g.ICP, ic0 = kq - tap * g.ICP;
+          const int fy = tap / g.FW, fx = tap - fy * g.FW;
+          const bool ok = m_ok && tap < g.taps && (unsigned)(iy0 + fy) < (unsigned)g.H &&
+                          (unsigned)(ix0 + fx) < (unsigned)g.W;
+          const float *q = g.In + base_off + (int64_t)ic0 * hw + fy * g.W + fx;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[4 * c + i] = (ok && ic0 + i < g.C) ? __ldg(q + i * hw) : 0.0f;
+        }
+      }
+    }
+    __device__ __forceinline__ void store(float4 *hi, int p) const { store_row16<LA>(v, hi, p); }
+  };
+
+  struct B : MatrixOperand<OP_KV, BN, LB> {
+    __device__ __forceinline__ void init(const Args &g) { this->setup(g.Wk, g.Kp, g.N, g.Kp); }
+    __device__ __forceinline__ void tile(const Args &, int t, int) { this->set_tile(t); }
+    __device__ __forceinline__ void load(const Args &, int ks, int p) { this->load_stage(ks, p); }
+  };
+
+  static __device__ __forceinline__ float activate(int act, float x) {
+    switch (act) {
+      case PB_RELU: return act_fwd<PB_RELU>(x);
+      case PB_LEAKY_RELU: return act_fwd<PB_LEAKY_RELU>(x);
+      case PB_SIGMOID: return act_fwd<PB_SIGMOID>(x);
+    }
+    return x;
+  }
+
+  static __device__ __forceinline__ void store1(const Args &g, int64_t m, int n, float acc) {
+    const int ohw = g.OH * g.OW;
+    const int64_t b = m / ohw;
+    const int pix = (int)(m - b * ohw);
+    const float val = acc + __ldg(g.Wref + (int64_t)n * (g.kref + 1) + g.kref);
+    const int64_t idx = (b * g.OC + n) * ohw + pix;
+    g.Out[idx] = val;
+    if (g.Out2) g.Out2[idx] = activate(g.act, val);
+  }
+
+  static __device__ __forceinline__ void store16(const Args &g, int m, int n0, const float (&v)[16],
+                                                 int nv) {
+    const int ohw = g.OH * g.OW;
+    const int b = m / ohw, pix = m - b * ohw;
+    const int64_t idx = ((int64_t)b * g.OC + n0) * ohw + pix;
+    const float *bias = g.Wref + (int64_t)n0 * (g.kref + 1) + g.kref;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < nv) {
+        const float val = v[j] + __ldg(bias + (int64_t)j * (g.kref + 1));
+        g.Out[idx + (int64_t)j * ohw] = val;
+        if (g.Out2) g.Out2[idx + (int64_t)j * ohw] = activate(g.act, val);
+      }
+    }
+  }
+};
+
+}  // namespace
+
+// Returns -1 outside the envelope (then the FFMA kernels run).  O2 != nullptr:
+// additionally writes act(O) (the following ActivationLayer's output).
+int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                            const float *W, float *O, float *O2, int act, int64_t batch) {
+  if (!umma_gemm_enabled()) return -1;
+  const int64_t C = l->depth, OC = l->num_filters;
+  const int64_t OW = conv_out_w(l), OH = conv_out_h(l);
+  const int64_t taps = l->filter_width * l->filter_height;
+  if (C > 8 && C % 16 != 0) return -1;
+  const int64_t ICP = C <= 4 ? 4 : (C <= 8 ? 8 : C);
+  const int64_t K = taps * ICP;
+  const int64_t M = batch * OH * OW;
+  if (M <= 0 || OC <= 0) return 0;
+  // worth a tensor-core launch?  (small products are latency-bound either way)
+  if (M * OC * K < ((int64_t)1 << 26) || M >= ((int64_t)1 << 31) - BM || OC * (K + BK) >= ((int64_t)1 << 31))
+    return -1;
+  const int Kp = pb_div_up(K, BK) * BK;
+  if (ensure_aux(ctx, (size_t)OC * Kp)) return 1;
+  retile_filters_kernel<<<pb_ew_grid(ctx, OC * Kp, 256), 256, 0, ctx->stream>>>(
+      W, ctx->aux, (int)OC, (int)C, (int)taps, (int)ICP, Kp);
+  PB_LAUNCHED(ctx);
+  ConvArgs g{};
+  g.In = I; g.Wk = ctx->aux; g.Wref = W; g.Out = O; g.Out2 = O2; g.act = act;
+  g.C = (int)C; g.H = (int)l->height; g.W = (int)l->width; g.OC = (int)OC;
+  g.OH = (int)OH; g.OW = (int)OW; g.FH = (int)l->filter_height; g.FW = (int)l->filter_width;
+  g.stride = (int)l->stride; g.pad = (int)l->padding;
+  g.ICP = (int)ICP; g.taps = (int)taps; g.Kp = Kp; g.kref = C * taps;
+  return launch_gemm<ConvPolicy>(ctx, g, (int)M, (int)OC, Kp);
+}
+
+}  // namespace pb

@@ -83,6 +83,12 @@ int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *conv, int 
                                 const pb_layer_desc *pool, const float *I, const float *W,
                                 float *O_conv, float *O_pool, int64_t batch);
 
+// conv_gemm_umma.cu: general implicit-GEMM tensor-core convolution (forward) for large
+// batched shapes, any filter / stride / padding; O2 != nullptr additionally receives
+// act(O), the output of a following ActivationLayer.  -1 outside the envelope.
+int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                            const float *W, float *O, float *O2, int act, int64_t batch);
+
 // Output extent of a convolution, nnet/convolution_layer.cc:36-44.
 static inline int64_t conv_out_w(const pb_layer_desc *l) {
   return (l->width - l->filter_width + 2 * l->padding) / l->stride + 1;

@@ -195,6 +195,21 @@ static int forward(pb_nnet *net, const float *d_in, int64_t batch) {
   const float *cur = d_in;
   for (size_t l = 0; l < net->layers.size(); ++l) {
     const float *W = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
+    // convolution + the ActivationLayer behind it in one kernel (both outputs are
+    // materialised: eval_layer_outputs_ keeps every layer's result, nnet.h:81-83)
+    if (net->fuse && batch >= 8 && net->layers[l].kind == PB_CONVOLUTION &&
+        l + 1 < net->layers.size() && net->layers[l + 1].kind == PB_ACTIVATION &&
+        net->layers[l + 1].n == net->no[l]) {
+      const int rc = conv_evaluate_gemm_umma(net->ctx, &net->layers[l], cur, W, net->outputs[l],
+                                             net->outputs[l + 1], net->layers[l + 1].activation,
+                                             batch);
+      if (rc > 0) return 1;
+      if (rc == 0) {
+        cur = net->outputs[l + 1];
+        l += 1;
+        continue;
+      }
+    }
     if (pb_layer_evaluate(net->ctx, &net->layers[l], cur, W, net->outputs[l], batch)) return 1;
     cur = net->outputs[l];
   }
