@@ -268,6 +268,10 @@ int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
 int pb_nnet_profile_step(pb_nnet *net, const float *d_ins, const float *d_expected,
                          int64_t batch, char *out, size_t cap);
 
+/* The same for one batched pb_nnet_evaluate (forward only). */
+int pb_nnet_profile_evaluate(pb_nnet *net, const float *d_in, int64_t batch, char *out,
+                             size_t cap);
+
 /* ------------------------------------------------------------------------
  * Measurement helpers (bench.py): peak FP32 FFMA throughput and HBM copy
  * bandwidth of this device, measured with CUDA events.

@@ -205,12 +205,14 @@ static int forward(pb_nnet *net, const float *d_in, int64_t batch) {
                                              batch);
       if (rc > 0) return 1;
       if (rc == 0) {
+        mark(net, layer_tag(net, (int)l) + "+" + layer_tag(net, (int)l + 1) + ":evaluate (tcgen05)");
         cur = net->outputs[l + 1];
         l += 1;
         continue;
       }
     }
     if (pb_layer_evaluate(net->ctx, &net->layers[l], cur, W, net->outputs[l], batch)) return 1;
+    mark(net, layer_tag(net, (int)l) + ":evaluate");
     cur = net->outputs[l];
   }
   return 0;
@@ -610,14 +612,14 @@ int pb_nnet_apply_deltas(pb_nnet *net) {
   return 0;
 }
 
-int pb_nnet_profile_step(pb_nnet *net, const float *d_ins, const float *d_expected, int64_t batch,
-                         char *out, size_t cap) {
-  PB_CHECK(net && out && cap > 2, "pb_nnet_profile_step: null");
+static void profile_begin(pb_nnet *net) {
   for (auto &m : net->marks) cudaEventDestroy(m.second);
   net->marks.clear();
   net->profiling = true;
   pb::mark(net, "start");
-  const int rc = pb_nnet_batch_train(net, d_ins, d_expected, batch);
+}
+
+static int profile_end(pb_nnet *net, int rc, char *out, size_t cap) {
   net->profiling = false;
   if (rc) return 1;
   PB_CUDA(cudaStreamSynchronize(net->ctx->stream));
@@ -631,9 +633,23 @@ int pb_nnet_profile_step(pb_nnet *net, const float *d_ins, const float *d_expect
   }
   for (auto &m : net->marks) cudaEventDestroy(m.second);
   net->marks.clear();
-  PB_CHECK(text.size() + 1 <= cap, "pb_nnet_profile_step: output buffer too small");
+  PB_CHECK(text.size() + 1 <= cap, "pb_nnet_profile: output buffer too small");
   memcpy(out, text.c_str(), text.size() + 1);
   return 0;
+}
+
+int pb_nnet_profile_step(pb_nnet *net, const float *d_ins, const float *d_expected, int64_t batch,
+                         char *out, size_t cap) {
+  PB_CHECK(net && out && cap > 2, "pb_nnet_profile_step: null");
+  profile_begin(net);
+  return profile_end(net, pb_nnet_batch_train(net, d_ins, d_expected, batch), out, cap);
+}
+
+int pb_nnet_profile_evaluate(pb_nnet *net, const float *d_in, int64_t batch, char *out,
+                             size_t cap) {
+  PB_CHECK(net && out && cap > 2, "pb_nnet_profile_evaluate: null");
+  profile_begin(net);
+  return profile_end(net, pb_nnet_evaluate(net, d_in, batch, nullptr), out, cap);
 }
 
 int pb_nnet_batch_train(pb_nnet *net, const float *d_ins, const float *d_expected,

@@ -26,8 +26,11 @@ import bench  # noqa: E402  (ClockSampler, step_profile)
 
 def mlp_model(pb, width, classes=10):
     m = pb.Architecture(width)
-    m.AddDenseLayer(width, pb.Relu)
-    m.AddDenseLayer(width, pb.Relu)
+    # Architecture(4096).AddDenseLayer(4096).AddDenseLayer(4096)
+    #   .AddDenseLayer(10, Identity).AddSoftmaxLayer(10) — AddDenseLayer(n) puts the
+    # builder's default Sigmoid behind the layer (architecture.h:63-74)
+    m.AddDenseLayer(width)
+    m.AddDenseLayer(width)
     m.AddDenseLayer(classes, pb.Identity)
     m.AddSoftmaxLayer(classes)
     return m
