@@ -22,24 +22,30 @@ namespace {
 
 using namespace ugemm;
 
+constexpr int kMaxTaps = 128;
+
 struct ConvArgs : GemmCore {
   const float *In;    // [batch][C][H][W]
   const float *Wk;    // re-tiled filters [OC][Kp], k' = tap*ICP + ic
-  const float *Wref;  // reference layout [OC][C*FH*FW + 1] (for the bias)
+  const float *bias;  // [OC], gathered from the reference layout by the pre-pass
   float *Out;         // [batch][OC][OH][OW]
   float *Out2;        // act(Out), nullable
   int act;
   int C, H, W, OC, OH, OW, FH, FW, stride, pad;
   int ICP;            // channels per tap in K order: 4, 8 or a multiple of 16
   int taps, Kp;
-  int64_t kref;       // C*FH*FW
+  uint16_t tap_yx[kMaxTaps];  // tap -> (fy << 8 | fx)
 };
 
 // Wk[oc][tap*ICP + ic] = Wref[oc][ic][tap], zero in the padding.
 __global__ void retile_filters_kernel(const float *__restrict__ Wref, float *__restrict__ Wk,
-                                      int OC, int C, int taps, int ICP, int Kp) {
+                                      float *__restrict__ bias, int OC, int C, int taps, int ICP,
+                                      int Kp) {
   const int64_t total = (int64_t)OC * Kp;
   const int64_t kref1 = (int64_t)C * taps + 1;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < OC;
+       t += (int64_t)gridDim.x * blockDim.x)
+    bias[t] = Wref[t * kref1 + kref1 - 1];
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t oc = t / Kp;
@@ -76,7 +82,8 @@ struct ConvPolicy {
         // one tap per stage, 16 consecutive channels
         const int per = g.ICP >> 4;
         const int tap = ks / per, icb = ks - tap * per;
-        const int fy = tap / g.FW, fx = tap - fy * g.FW;
+        const int yx = g.tap_yx[min(tap, kMaxTaps - 1)];
+        const int fy = yx >> 8, fx = yx & 255;
         const bool ok = m_ok && tap < g.taps && (unsigned)(iy0 + fy) < (unsigned)g.H &&
                         (unsigned)(ix0 + fx) < (unsigned)g.W;
         const float *q = g.In + base_off + (int64_t)(icb * 16) * hw + fy * g.W + fx;
@@ -92,8 +99,9 @@ struct ConvPolicy {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int kq = ks * 16 + 4 * c;
-          const int tap = kq / g.ICP, ic0 = kq - tap * g.ICP;
-          const int fy = tap / g.FW, fx = tap - fy * g.FW;
+          const int tap = g.ICP == 4 ? kq >> 2 : kq >> 3, ic0 = kq & (g.ICP - 1);
+          const int yx = g.tap_yx[min(tap, kMaxTaps - 1)];
+          const int fy = yx >> 8, fx = yx & 255;
           const bool ok = m_ok && tap < g.taps && (unsigned)(iy0 + fy) < (unsigned)g.H &&
                           (unsigned)(ix0 + fx) < (unsigned)g.W;
           const float *q = g.In + base_off + (int64_t)ic0 * hw + fy * g.W + fx;
@@ -106,42 +114,68 @@ struct ConvPolicy {
   };
 
   struct B : MatrixOperand<OP_KV, BN, LB> {
-    __device__ __forceinline__ void init(const Args &g) { this->setup(g.Wk, g.Kp, g.N, g.Kp); }
+    __device__ __forceinline__ void init(const Args &g) {
+      this->setup(g.Wk, g.Kp, g.N, g.Kp, g.mma_n);
+    }
     __device__ __forceinline__ void tile(const Args &, int t, int) { this->set_tile(t); }
     __device__ __forceinline__ void load(const Args &, int ks, int p) { this->load_stage(ks, p); }
   };
 
-  static __device__ __forceinline__ float activate(int act, float x) {
-    switch (act) {
-      case PB_RELU: return act_fwd<PB_RELU>(x);
-      case PB_LEAKY_RELU: return act_fwd<PB_LEAKY_RELU>(x);
-      case PB_SIGMOID: return act_fwd<PB_SIGMOID>(x);
-    }
-    return x;
+  template <int ACT>
+  static __device__ __forceinline__ void store_act(float *o2, int ohw, const float (&val)[16],
+                                                   int nv) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j, o2 += ohw)
+      if (j < nv) *o2 = act_fwd<ACT>(val[j]);
   }
 
   static __device__ __forceinline__ void store1(const Args &g, int64_t m, int n, float acc) {
     const int ohw = g.OH * g.OW;
     const int64_t b = m / ohw;
     const int pix = (int)(m - b * ohw);
-    const float val = acc + __ldg(g.Wref + (int64_t)n * (g.kref + 1) + g.kref);
+    const float val = acc + __ldg(g.bias + n);
     const int64_t idx = (b * g.OC + n) * ohw + pix;
     g.Out[idx] = val;
-    if (g.Out2) g.Out2[idx] = activate(g.act, val);
+    if (g.Out2) {
+      float a = val;
+      if (g.act == PB_RELU) a = act_fwd<PB_RELU>(val);
+      else if (g.act == PB_LEAKY_RELU) a = act_fwd<PB_LEAKY_RELU>(val);
+      else if (g.act == PB_SIGMOID) a = act_fwd<PB_SIGMOID>(val);
+      g.Out2[idx] = a;
+    }
   }
 
+  // 16 output channels of one pixel: lanes are consecutive pixels, so every store
+  // instruction of the warp writes one 128-byte line of one channel plane.
   static __device__ __forceinline__ void store16(const Args &g, int m, int n0, const float (&v)[16],
                                                  int nv) {
     const int ohw = g.OH * g.OW;
     const int b = m / ohw, pix = m - b * ohw;
     const int64_t idx = ((int64_t)b * g.OC + n0) * ohw + pix;
-    const float *bias = g.Wref + (int64_t)n0 * (g.kref + 1) + g.kref;
+    float val[16];
+    if (nv == 16) {
+      const float4 *bp = reinterpret_cast<const float4 *>(g.bias + n0);  // n0 % 16 == 0
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < nv) {
-        const float val = v[j] + __ldg(bias + (int64_t)j * (g.kref + 1));
-        g.Out[idx + (int64_t)j * ohw] = val;
-        if (g.Out2) g.Out2[idx + (int64_t)j * ohw] = activate(g.act, val);
+      for (int q = 0; q < 4; ++q) {
+        const float4 bq = __ldg(bp + q);
+        val[4 * q] = v[4 * q] + bq.x; val[4 * q + 1] = v[4 * q + 1] + bq.y;
+        val[4 * q + 2] = v[4 * q + 2] + bq.z; val[4 * q + 3] = v[4 * q + 3] + bq.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) val[j] = j < nv ? v[j] + __ldg(g.bias + n0 + j) : 0.0f;
+    }
+    float *o = g.Out + idx;
+#pragma unroll
+    for (int j = 0; j < 16; ++j, o += ohw)
+      if (j < nv) *o = val[j];
+    if (g.Out2) {
+      float *o2 = g.Out2 + idx;
+      switch (g.act) {
+        case PB_RELU: store_act<PB_RELU>(o2, ohw, val, nv); break;
+        case PB_LEAKY_RELU: store_act<PB_LEAKY_RELU>(o2, ohw, val, nv); break;
+        case PB_SIGMOID: store_act<PB_SIGMOID>(o2, ohw, val, nv); break;
+        default: store_act<PB_IDENTITY>(o2, ohw, val, nv); break;
       }
     }
   }
@@ -166,16 +200,20 @@ int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float
   if (M * OC * K < ((int64_t)1 << 26) || M >= ((int64_t)1 << 31) - BM || OC * (K + BK) >= ((int64_t)1 << 31))
     return -1;
   const int Kp = pb_div_up(K, BK) * BK;
-  if (ensure_aux(ctx, (size_t)OC * Kp)) return 1;
+  if (taps > kMaxTaps || l->filter_width > 255 || l->filter_height > 255) return -1;
+  const size_t bias_off = ((size_t)OC * Kp + 3) & ~(size_t)3;  // keeps the bias 16-byte aligned
+  if (ensure_aux(ctx, bias_off + (size_t)OC + 16)) return 1;
   retile_filters_kernel<<<pb_ew_grid(ctx, OC * Kp, 256), 256, 0, ctx->stream>>>(
-      W, ctx->aux, (int)OC, (int)C, (int)taps, (int)ICP, Kp);
+      W, ctx->aux, ctx->aux + bias_off, (int)OC, (int)C, (int)taps, (int)ICP, Kp);
   PB_LAUNCHED(ctx);
   ConvArgs g{};
-  g.In = I; g.Wk = ctx->aux; g.Wref = W; g.Out = O; g.Out2 = O2; g.act = act;
+  g.In = I; g.Wk = ctx->aux; g.bias = ctx->aux + bias_off; g.Out = O; g.Out2 = O2; g.act = act;
+  for (int t = 0; t < (int)taps; ++t)
+    g.tap_yx[t] = (uint16_t)(((t / l->filter_width) << 8) | (t % l->filter_width));
   g.C = (int)C; g.H = (int)l->height; g.W = (int)l->width; g.OC = (int)OC;
   g.OH = (int)OH; g.OW = (int)OW; g.FH = (int)l->filter_height; g.FW = (int)l->filter_width;
   g.stride = (int)l->stride; g.pad = (int)l->padding;
-  g.ICP = (int)ICP; g.taps = (int)taps; g.Kp = Kp; g.kref = C * taps;
+  g.ICP = (int)ICP; g.taps = (int)taps; g.Kp = Kp;
   return launch_gemm<ConvPolicy>(ctx, g, (int)M, (int)OC, Kp);
 }
 

@@ -38,12 +38,12 @@ template <int AMODE, int BMODE>
 struct DensePolicy {
   using Args = DenseArgs;
   struct A : MatrixOperand<AMODE, BM, LA> {
-    __device__ __forceinline__ void init(const Args &g) { this->setup(g.A, g.lda, g.M, g.K); }
+    __device__ __forceinline__ void init(const Args &g) { this->setup(g.A, g.lda, g.M, g.K, BM); }
     __device__ __forceinline__ void tile(const Args &, int t, int) { this->set_tile(t); }
     __device__ __forceinline__ void load(const Args &, int ks, int p) { this->load_stage(ks, p); }
   };
   struct B : MatrixOperand<BMODE, BN, LB> {
-    __device__ __forceinline__ void init(const Args &g) { this->setup(g.B, g.ldb, g.N, g.K); }
+    __device__ __forceinline__ void init(const Args &g) { this->setup(g.B, g.ldb, g.N, g.K, g.mma_n); }
     __device__ __forceinline__ void tile(const Args &, int t, int) { this->set_tile(t); }
     __device__ __forceinline__ void load(const Args &, int ks, int p) { this->load_stage(ks, p); }
   };
@@ -70,15 +70,30 @@ struct DensePolicy {
                         v[4 * q + 2] + b[4 * q + 2], v[4 * q + 3] + b[4 * q + 3]);
       return;
     }
-    const float rate = g.epi == EPI_UPDATE ? g.lr[0] : 0.0f;
+    if (g.epi == EPI_UPDATE) {
+      // out = W - lr*g | -lr*g | out - lr*g  (back_prop.kernel.cl:28-44 + combine)
+      const float rate = g.lr[0];
+      const float *wrow = g.Wold + (int64_t)m * g.ldc + n0;
+      if (g.mode == PB_NEW_WEIGHTS) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) crow[j] = wrow[j] - rate * v[j];
+      } else if (g.mode == PB_WEIGHT_DELTAS) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) crow[j] = -rate * v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) crow[j] += -rate * v[j];
+      }
+      return;
+    }
+    const float *bp = g.bias + (int64_t)n0 * g.ldbias;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      if (j < nv) {
-        if (g.epi == EPI_BIAS) crow[j] = __ldg(g.bias + (int64_t)(n0 + j) * g.ldbias) + v[j];
-        else if (g.epi == EPI_UPDATE)
-          apply_update(g.mode, g.C, g.Wold, (int64_t)m * g.ldc + n0 + j, rate, v[j]);
-        else crow[j] = v[j];
-      }
+      if (j < nv) crow[j] = g.epi == EPI_BIAS ? __ldg(bp) + v[j] : v[j];
+      bp += g.ldbias;
     }
   }
 };

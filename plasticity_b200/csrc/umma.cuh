@@ -33,16 +33,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware until the phase completes or the time
+  // hint expires, so waiting warps do not spin on the issue slots of working ones.
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 

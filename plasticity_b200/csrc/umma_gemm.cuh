@@ -100,16 +100,18 @@ struct MatrixOperand {
   const float *base;
   int64_t ld;
   int rows_total, k_total, row0;
+  int rows_active;  // rows of the tile the MMA reads (mma_n for B): the rest is not touched
   float v[NV];
 
-  __device__ __forceinline__ void setup(const float *b, int64_t l, int rows, int k) {
-    base = b; ld = l; rows_total = rows; k_total = k;
+  __device__ __forceinline__ void setup(const float *b, int64_t l, int rows, int k, int active) {
+    base = b; ld = l; rows_total = rows; k_total = k; rows_active = active;
   }
   __device__ __forceinline__ void set_tile(int tile) { row0 = tile * ROWS; }
 
   __device__ __forceinline__ void load_stage(int ks, int p) {
     const int k0 = ks * BK, k_end = k_total;
-    const bool interior = row0 + ROWS <= rows_total && k0 + BK <= k_end;
+    const bool interior =
+        row0 + ((rows_active + 31) & ~31) <= rows_total && k0 + BK <= k_end;
     if (MODE == OP_KV) {
       const int r = row0 + (p >> 2), k = k0 + 4 * (p & 3);
       const float *q = base + (int64_t)r * ld + k;
@@ -117,14 +119,17 @@ struct MatrixOperand {
       if (interior) {
 #pragma unroll
         for (int j = 0; j < NV / 4; ++j, q += step) {
-          const float4 x = __ldg(reinterpret_cast<const float4 *>(q));
-          v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+          if (32 * j < rows_active) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(q));
+            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+          }
         }
       } else {
 #pragma unroll
         for (int j = 0; j < NV / 4; ++j, q += step) {
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r + 32 * j < rows_total && k < k_end) x = __ldg(reinterpret_cast<const float4 *>(q));
+          if (32 * j < rows_active && r + 32 * j < rows_total && k < k_end)
+            x = __ldg(reinterpret_cast<const float4 *>(q));
           v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
         }
       }
@@ -137,14 +142,16 @@ struct MatrixOperand {
         for (int kk = 0; kk < BK; ++kk, q += ld)
 #pragma unroll
           for (int h = 0; h < H; ++h)
-            v[4 * (H * (kk >> 2) + h) + (kk & 3)] = __ldg(q + h * kGroupThreads);
+            if (h * kGroupThreads < rows_active)
+              v[4 * (H * (kk >> 2) + h) + (kk & 3)] = __ldg(q + h * kGroupThreads);
       } else {
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk, q += ld)
 #pragma unroll
           for (int h = 0; h < H; ++h)
             v[4 * (H * (kk >> 2) + h) + (kk & 3)] =
-                (r + h * kGroupThreads < rows_total && k0 + kk < k_end)
+                (h * kGroupThreads < rows_active && r + h * kGroupThreads < rows_total &&
+                 k0 + kk < k_end)
                     ? __ldg(q + h * kGroupThreads) : 0.0f;
       }
     } else {
@@ -153,11 +160,12 @@ struct MatrixOperand {
       const int64_t step = 8 * ld;
       if (interior) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j, q += step) v[j] = __ldg(q);
+        for (int j = 0; j < NV; ++j, q += step)
+          if (8 * j < rows_active) v[j] = __ldg(q);
       } else {
 #pragma unroll
         for (int j = 0; j < NV; ++j, q += step)
-          v[j] = (r + 8 * j < rows_total && k < k_end) ? __ldg(q) : 0.0f;
+          v[j] = (8 * j < rows_active && r + 8 * j < rows_total && k < k_end) ? __ldg(q) : 0.0f;
       }
     }
   }
@@ -169,9 +177,11 @@ struct MatrixOperand {
       float *l = h + CHUNKS * L * 4;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const float xh = split_hi(v[j]);
-        h[32 * j] = xh;
-        l[32 * j] = v[j] - xh;
+        if (8 * j < rows_active) {
+          const float xh = split_hi(v[j]);
+          h[32 * j] = xh;
+          l[32 * j] = v[j] - xh;
+        }
       }
     } else {
       // KV: value group j = (row (p>>2) + 32j, chunk p&3); MN: group j = (chunk j/H, row p + 128(j%H))
@@ -181,6 +191,7 @@ struct MatrixOperand {
 #pragma unroll
       for (int j = 0; j < NV / 4; ++j) {
         const int off = MODE == OP_KV ? 32 * j : (j / H) * L + (j % H) * kGroupThreads;
+        if ((MODE == OP_KV ? 32 * j : (j % H) * kGroupThreads) >= rows_active) continue;
         const float h0 = split_hi(v[4 * j]), h1 = split_hi(v[4 * j + 1]),
                     h2 = split_hi(v[4 * j + 2]), h3 = split_hi(v[4 * j + 3]);
         hi[off] = make_float4(h0, h1, h2, h3);
@@ -191,7 +202,7 @@ struct MatrixOperand {
 };
 
 template <class P>
-__global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const typename P::Args g) {
+__global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_constant__ typename P::Args g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float4 *stage_s = reinterpret_cast<float4 *>(smem_raw);  // [STAGES][STAGE_UNITS]
   uint64_t *bars = reinterpret_cast<uint64_t *>(stage_s + STAGES * STAGE_UNITS);
