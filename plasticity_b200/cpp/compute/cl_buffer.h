@@ -62,6 +62,15 @@ class ClBuffer {
     CHECK_NOTNULL(ctx_);
     Adopt(dptr);
   }
+  // Non-owning window onto n floats of another device allocation (samples stored back
+  // to back): same state machine, nothing is freed when the view dies.
+  static std::unique_ptr<ClBuffer> View(pb_context *ctx, float *dptr, size_t n) {
+    auto v = std::make_unique<ClBuffer>(ctx);
+    v->state_ = GPU;
+    v->gpu_size_ = n;
+    v->gpu_buffer_ = std::shared_ptr<float>(dptr, [](float *) {});
+    return v;
+  }
   ClBuffer(const ClBuffer &other)
       : state_(other.state_), cpu_buffer_(other.cpu_buffer_), ctx_(other.ctx_),
         gpu_size_(other.gpu_size_) {

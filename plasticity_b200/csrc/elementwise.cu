@@ -150,6 +150,34 @@ __global__ void pool_fwd_kernel(const float *__restrict__ I, float *__restrict__
   }
 }
 
+// Exact 2x2 windows, W % 4 == 0: one thread reads a float4 from each of the two window
+// rows and writes two outputs — every access is a full-width vector, the kernel runs at
+// HBM speed.  Same strict '>' scan order as above (row 0 then row 1, left to right).
+__global__ void pool2x2_fwd_kernel(const float *__restrict__ I, float *__restrict__ O, int W,
+                                   int H, int64_t total /* batch*D*(H/2)*(W/4) */) {
+  const int qw = W >> 2, oh = H >> 1;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t plane = t / (qw * oh);
+    const int rem = (int)(t - plane * (qw * oh));
+    const int orow = rem / qw, q = rem - orow * qw;
+    const float *src = I + plane * (int64_t)W * H + (int64_t)(2 * orow) * W + 4 * q;
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(src + W));
+    float m0 = -INFINITY, m1 = -INFINITY;
+    if (a.x > m0) m0 = a.x;
+    if (a.y > m0) m0 = a.y;
+    if (b.x > m0) m0 = b.x;
+    if (b.y > m0) m0 = b.y;
+    if (a.z > m1) m1 = a.z;
+    if (a.w > m1) m1 = a.w;
+    if (b.z > m1) m1 = b.z;
+    if (b.w > m1) m1 = b.w;
+    *reinterpret_cast<float2 *>(O + plane * (int64_t)(W >> 1) * oh + (int64_t)orow * (W >> 1) +
+                                2 * q) = make_float2(m0, m1);
+  }
+}
+
 __global__ void pool_bwd_kernel(const float *__restrict__ I, const float *__restrict__ G,
                                 float *__restrict__ dI, int W, int H, int D, int ow,
                                 int oh, int64_t total) {
@@ -180,6 +208,14 @@ int pool_evaluate(pb_context *ctx, const pb_layer_desc *l, const float *I, float
                   int64_t batch) {
   const int64_t total = batch * l->out_width * l->out_height * l->depth;
   if (total == 0) return 0;
+  if (l->out_width * 2 == l->width && l->out_height * 2 == l->height && (l->width & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(I) & 15) == 0 && (reinterpret_cast<uintptr_t>(O) & 7) == 0) {
+    const int64_t quads = total / 2;
+    pool2x2_fwd_kernel<<<pb_ew_grid(ctx, quads, 256), 256, 0, ctx->stream>>>(
+        I, O, (int)l->width, (int)l->height, quads);
+    PB_LAUNCHED(ctx);
+    return 0;
+  }
   pool_fwd_kernel<<<pb_ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(
       I, O, (int)l->width, (int)l->height, (int)l->depth, (int)l->out_width,
       (int)l->out_height, total);

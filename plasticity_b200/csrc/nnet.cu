@@ -152,7 +152,7 @@ static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
 // Reverse loop over the fused plan; same per-layer order as backward().
 static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool first_chunk,
                           const std::vector<const float *> &layer_in,
-                          const std::vector<char> &fused_fwd, int top) {
+                          const std::vector<char> &fused_fwd, int top, bool in_place) {
   const int n = (int)net->layers.size();
   for (int l = top; l >= 0; --l) {
     const pb_layer_desc *L = &net->layers[l];
@@ -180,11 +180,12 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
     if (pb_layer_input_delta(net->ctx, L, in, W, g, ng, batch)) return 1;
     mark(net, layer_tag(net, l) + ":input_delta");
     if (net->nw[l] > 0) {
-      const int m = first_chunk ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
-      if (pb_layer_weight_update(net->ctx, L, in, W, g, net->deltas + net->w_off[l], net->lr, m,
-                                 batch))
-        return 1;
-      mark(net, layer_tag(net, l) + ":weight_update");
+      // in_place: W <- W - lr * sum_b grad_b directly (the layer's input_delta, the only
+      // later reader of W in this step, is already queued ahead on the in-order stream)
+      const int m = in_place ? PB_NEW_WEIGHTS : first_chunk ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
+      float *out = in_place ? W : net->deltas + net->w_off[l];
+      if (pb_layer_weight_update(net->ctx, L, in, W, g, out, net->lr, m, batch)) return 1;
+      mark(net, layer_tag(net, l) + (in_place ? ":weight_update (in place)" : ":weight_update"));
     }
     float *t = g; g = ng; ng = t;
   }
@@ -536,10 +537,12 @@ int pb_nnet_train_loop(pb_nnet *net, const float *d_ins, const float *d_expected
   return 0;
 }
 
-int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_expected,
-                            int64_t batch) {
-  PB_CHECK(net && d_ins && d_expected, "pb_nnet_batch_gradients: null");
-  PB_CHECK(batch >= 1, "pb_nnet_batch_gradients: empty batch");
+// The batched gradient pass.  in_place == false: fills the delta buffer (-lr * sum_b
+// grad_b, CalculateGradients); in_place == true (one chunk only): every layer's weight
+// kernel writes W - lr * sum_b grad_b straight into W — BatchTrain without the delta
+// round trip (nnet.h:652-665 VectorAccumulate fused into the weight kernels).
+static int batch_pass(pb_nnet *net, const float *d_ins, const float *d_expected, int64_t batch,
+                      bool in_place) {
   pb_context *ctx = net->ctx;
   const int64_t nin = net->ni[0], nout = net->no.back();
   // Batches larger than max_batch run as chunks; every chunk sees the same
@@ -569,9 +572,9 @@ int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_exp
         if (rc == 0) {
           pb::mark(net, pb::layer_tag(net, h) + ".." + pb::layer_tag(net, n - 1) +
                             ":evaluate+error_gradients+input_delta (head)");
-          const int m = b0 == 0 ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
-          if (pb_layer_weight_update(ctx, &net->layers[h], X, W, ng, net->deltas + net->w_off[h],
-                                     net->lr, m, nb))
+          const int m = in_place ? PB_NEW_WEIGHTS : b0 == 0 ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
+          if (pb_layer_weight_update(ctx, &net->layers[h], X, W, ng,
+                                     in_place ? W : net->deltas + net->w_off[h], net->lr, m, nb))
             return 1;
           pb::mark(net, pb::layer_tag(net, h) + ":weight_update");
           top = h - 1;
@@ -591,7 +594,7 @@ int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_exp
           pb_error_gradients(ctx, net->loss, nout, net->outputs.back(), d_expected + b0 * nout,
                              net->grad_a, nb))
         return 1;
-      if (pb::backward_fused(net, nb, g, ng, b0 == 0, layer_in, fused_fwd, top)) return 1;
+      if (pb::backward_fused(net, nb, g, ng, b0 == 0, layer_in, fused_fwd, top, in_place)) return 1;
       continue;
     }
     if (pb::forward(net, in, nb)) return 1;
@@ -599,10 +602,18 @@ int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_exp
                            net->grad_a, nb))
       return 1;
     float *g = nullptr;
-    if (pb::backward(net, in, nb, net->grad_a, net->grad_b, PB_WEIGHT_DELTAS, b0 == 0, &g))
+    if (pb::backward(net, in, nb, net->grad_a, net->grad_b,
+                     in_place ? PB_NEW_WEIGHTS : PB_WEIGHT_DELTAS, b0 == 0, &g))
       return 1;
   }
   return 0;
+}
+
+int pb_nnet_batch_gradients(pb_nnet *net, const float *d_ins, const float *d_expected,
+                            int64_t batch) {
+  PB_CHECK(net && d_ins && d_expected, "pb_nnet_batch_gradients: null");
+  PB_CHECK(batch >= 1, "pb_nnet_batch_gradients: empty batch");
+  return batch_pass(net, d_ins, d_expected, batch, false);
 }
 
 int pb_nnet_apply_deltas(pb_nnet *net) {
@@ -654,7 +665,12 @@ int pb_nnet_profile_evaluate(pb_nnet *net, const float *d_in, int64_t batch, cha
 
 int pb_nnet_batch_train(pb_nnet *net, const float *d_ins, const float *d_expected,
                         int64_t batch) {
-  if (pb_nnet_batch_gradients(net, d_ins, d_expected, batch)) return 1;
+  PB_CHECK(net && d_ins && d_expected, "pb_nnet_batch_train: null");
+  PB_CHECK(batch >= 1, "pb_nnet_batch_train: empty batch");
+  // One chunk: the SGD update is fused into the weight-gradient kernels.  Several chunks
+  // must all see the batch-start weights, so they go through the delta buffer.
+  if (batch <= net->max_batch && net->fuse) return batch_pass(net, d_ins, d_expected, batch, true);
+  if (batch_pass(net, d_ins, d_expected, batch, false)) return 1;
   return pb_nnet_apply_deltas(net);
 }
 

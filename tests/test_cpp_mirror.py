@@ -51,3 +51,36 @@ def test_reference_circle_test_learns():
     assert len(pts) == 1000
     ok = sum(((float(x) ** 2 + float(y) ** 2 <= 1.0) == (float(s) > 0.5)) for x, y, s in pts)
     assert ok >= 900, f"only {ok}/1000 probe points classified correctly"
+
+
+def test_cifar_driver_trains_saves_and_reloads(tmp_path):
+    """plasticity_b200/cpp/apps/cifar_train.cc — the flow of nnet/cifar_test.cc (loader format,
+    signed-byte L2 normalisation, one-hot targets, the 13-layer model, progress print,
+    weight file save / load, --short) on records in the CIFAR binary format generated in
+    memory: minibatch training must learn the synthetic rule, the saved weight file must
+    reload through LoadWeightsFromString and reproduce the accuracy with --short, and the
+    strict per-sample SGD mode (the reference's loop) must run."""
+    exe = os.path.join(HERE, "cifar_train")
+    assert os.path.exists(exe), "tests/cpp/cifar_train missing: run __graft_entry__.build()"
+    wf = str(tmp_path / "weights.json")
+    open(wf, "w").close()  # "Provided weight file is empty. Initializing with random weights"
+    r = run(exe, wf, "--synthetic", "6000", "--epochs", "6", "--batch", "10", "--lr", "0.005",
+            "--examples", "500", timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Training rate (samples per second):" in r.stdout
+    m = re.search(r"Examples correct: (\d+) / (\d+)", r.stdout)
+    assert m, r.stdout[-1000:]
+    acc = int(m.group(1)) / int(m.group(2))
+    assert acc > 0.9, f"minibatch training reached only {acc:.2%} on the synthetic rule"
+    assert os.path.getsize(wf) > 100000
+    r2 = run(exe, wf, "--synthetic", "6000", "--short", "--examples", "500")
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    assert "Number of Epochs: 0" in r2.stdout and "Loading weights from file" in r2.stdout
+    m2 = re.search(r"Examples correct: (\d+) / (\d+)", r2.stdout)
+    assert m2 and m2.group(1) == m.group(1), (m.groups(), m2 and m2.groups())
+    r3 = run(exe, "--synthetic", "5000", "--epochs", "2", "--lr", "0.05", "--examples", "200",
+             timeout=900)
+    assert r3.returncode == 0, r3.stderr[-2000:]
+    assert "Training rate (samples per second):" in r3.stdout
+    m3 = re.search(r"Examples correct: (\d+) / (\d+)", r3.stdout)
+    assert m3 and int(m3.group(1)) / int(m3.group(2)) > 0.9, r3.stdout[-500:]
