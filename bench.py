@@ -158,7 +158,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -441,11 +441,25 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        emit(line)
     return 0
 
 
 def main():
+    # Libraries (NCCL's version banner, torchrun notices) print to fd 1; the contract is
+    # ONE JSON line on stdout, so everything else is sent to stderr and the line is
+    # written to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    rc, line = _main()
+    if line is not None:
+        real_stdout.write(line + "\n")
+        real_stdout.flush()
+    return rc
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -460,8 +474,17 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+        rc = run_reference(args)
+    else:
+        rc = run_ours(args)
+    return rc, _LINE[0]
+
+
+_LINE = [None]
+
+
+def emit(line):
+    _LINE[0] = json.dumps(line)
 
 
 if __name__ == "__main__":

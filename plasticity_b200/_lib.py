@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libplasticity_b200.so")
+# PB_LIB_PATH: an alternative build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("PB_LIB_PATH") or os.path.join(HERE, "lib", "libplasticity_b200.so")
 
 fp = C.POINTER(C.c_float)
 dp = C.POINTER(C.c_double)

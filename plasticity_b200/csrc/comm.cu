@@ -39,6 +39,11 @@ struct pb_comm {
   void *peers[kMaxP2pRanks] = {nullptr};
   uint32_t epoch = 0;
   int *d_timeout = nullptr;     // set by the kernel if a peer never showed up
+  // large delta buffers: per-layer all-reduce on a second stream, overlapped with the
+  // rest of the backward pass (last layer first)
+  cudaStream_t comm_stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t events_used = 0;
 };
 
 namespace pb {
@@ -196,6 +201,38 @@ static int p2p_setup(pb_comm *c, int64_t n) {
   return 0;
 }
 
+__global__ void accumulate_slice_kernel(float *__restrict__ w, const float *__restrict__ d,
+                                        int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    w[i] += d[i];
+}
+
+// delta_hook_fn: layer's slice of the delta buffer is complete on the compute stream ->
+// all-reduce it and apply it to the weights on the communication stream.  Every later
+// reader of these weights in this step (the layer's input_delta) is queued BEFORE the
+// event, the next step waits for the communication stream (pb_nnet_batch_train_dp).
+static int overlap_hook(void *user, int layer, float *d_delta, float *d_weights, int64_t n) {
+  (void)layer;
+  pb_comm *c = (pb_comm *)user;
+  NcclApi *api = nccl_api();
+  PB_CHECK(api, "pb_nnet_batch_train_dp: NCCL unavailable");
+  if (c->events_used == c->events.size()) {
+    cudaEvent_t e;
+    PB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->events.push_back(e);
+  }
+  cudaEvent_t ev = c->events[c->events_used++];
+  PB_CUDA(cudaEventRecord(ev, c->ctx->stream));
+  PB_CUDA(cudaStreamWaitEvent(c->comm_stream, ev, 0));
+  PB_NCCL(api, api->AllReduce(d_delta, d_delta, (size_t)n, ncclFloat, ncclSum, c->comm,
+                              c->comm_stream));
+  accumulate_slice_kernel<<<pb_ew_grid(c->ctx, n, 256), 256, 0, c->comm_stream>>>(d_weights,
+                                                                                 d_delta, n);
+  PB_LAUNCHED(c->ctx);
+  return 0;
+}
+
 }  // namespace pb
 
 extern "C" {
@@ -240,6 +277,11 @@ int pb_comm_destroy(pb_comm *comm) {
     cudaStreamSynchronize(comm->ctx->stream);
     for (int r = 0; r < comm->n_ranks; ++r)
       if (r != comm->rank && comm->peers[r]) cudaIpcCloseMemHandle(comm->peers[r]);
+    if (comm->comm_stream) {
+      cudaStreamSynchronize(comm->comm_stream);
+      cudaStreamDestroy(comm->comm_stream);
+    }
+    for (cudaEvent_t e : comm->events) cudaEventDestroy(e);
     if (comm->local) cudaFree(comm->local);
     if (comm->d_timeout) cudaFree(comm->d_timeout);
     api->CommDestroy(comm->comm);
@@ -261,10 +303,39 @@ int pb_comm_allreduce_sum(pb_comm *comm, float *d_buf, int64_t n) {
 int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
                            const float *d_expected, int64_t local_batch) {
   PB_CHECK(net && comm, "pb_nnet_batch_train_dp: null");
-  if (pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch)) return 1;
   float *deltas = nullptr;
   int64_t n = 0;
   if (pb_nnet_deltas_device(net, &deltas) || pb_nnet_total_weights(net, &n)) return 1;
+  static const bool overlap = [] {
+    const char *e = getenv("PB_DP_OVERLAP");
+    return !(e && e[0] == '0');
+  }();
+  if (comm->n_ranks > 1 && n > kMaxP2pFloats && overlap) {
+    // Bandwidth-bound exchange (the 4096-wide MLP: 134 MB): one all-reduce per layer,
+    // started as soon as that layer's weight gradient is done — last layer first — on a
+    // high-priority second stream, so the transfer of layer l overlaps the backward
+    // kernels of layers l-1, l-2, ...
+    if (!comm->comm_stream) {
+      int lo = 0, hi = 0;
+      PB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      PB_CUDA(cudaStreamCreateWithPriority(&comm->comm_stream, cudaStreamNonBlocking, hi));
+    }
+    comm->events_used = 0;
+    pb::nnet_set_delta_hook(net, pb::overlap_hook, comm);
+    const int rc = pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch);
+    pb::nnet_set_delta_hook(net, nullptr, nullptr);
+    if (rc) return 1;
+    if (comm->events_used == comm->events.size()) {
+      cudaEvent_t e;
+      PB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      comm->events.push_back(e);
+    }
+    cudaEvent_t done = comm->events[comm->events_used++];
+    PB_CUDA(cudaEventRecord(done, comm->comm_stream));
+    PB_CUDA(cudaStreamWaitEvent(comm->ctx->stream, done, 0));
+    return 0;
+  }
+  if (pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch)) return 1;
   if (comm->n_ranks > 1 && n <= kMaxP2pFloats) {
     if (comm->p2p_state == 0 && pb::p2p_setup(comm, n)) return 1;
     if (comm->p2p_state == 1 && comm->p2p_n == n) {

@@ -24,7 +24,15 @@ struct pb_context {
   size_t aux_elems = 0;
 };
 
+struct pb_nnet;
+
 namespace pb {
+
+// Called by the batched gradient pass right after the kernels that complete layer
+// `layer`'s slice of the delta buffer have been queued (last chunk only): the data-parallel
+// driver starts that slice's all-reduce while the earlier layers' backward still runs.
+typedef int (*delta_hook_fn)(void *user, int layer, float *d_delta, float *d_weights, int64_t n);
+void nnet_set_delta_hook(pb_nnet *net, delta_hook_fn hook, void *user);
 
 void set_error(const std::string &msg);
 int fail(const std::string &msg);

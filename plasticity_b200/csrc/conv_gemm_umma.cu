@@ -57,6 +57,8 @@ __global__ void retile_filters_kernel(const float *__restrict__ Wref, float *__r
 
 struct ConvPolicy {
   using Args = ConvArgs;
+  static constexpr bool kEpiTranspose = false;
+  static constexpr int kEpiCols = 16;
 
   // One output pixel per thread (lanes along M), 16 k values of the stage each.
   struct A {
@@ -121,14 +123,6 @@ struct ConvPolicy {
     __device__ __forceinline__ void load(const Args &, int ks, int p) { this->load_stage(ks, p); }
   };
 
-  template <int ACT>
-  static __device__ __forceinline__ void store_act(float *o2, int ohw, const float (&val)[16],
-                                                   int nv) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j, o2 += ohw)
-      if (j < nv) *o2 = act_fwd<ACT>(val[j]);
-  }
-
   static __device__ __forceinline__ void store1(const Args &g, int64_t m, int n, float acc) {
     const int ohw = g.OH * g.OW;
     const int64_t b = m / ohw;
@@ -147,8 +141,18 @@ struct ConvPolicy {
 
   // 16 output channels of one pixel: lanes are consecutive pixels, so every store
   // instruction of the warp writes one 128-byte line of one channel plane.
-  static __device__ __forceinline__ void store16(const Args &g, int m, int n0, const float (&v)[16],
-                                                 int nv) {
+  template <int ACT>
+  static __device__ __forceinline__ void store_act(float *o2, int ohw, const float (&val)[16],
+                                                   int nv) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j, o2 += ohw)
+      if (j < nv) *o2 = act_fwd<ACT>(val[j]);
+  }
+
+  static __device__ __forceinline__ void store_cols(const Args &g, int row0, int lane, int n0,
+                                                    const float (&v)[16], int nv, float *) {
+    const int m = row0 + lane;
+    if (m >= g.M) return;
     const int ohw = g.OH * g.OW;
     const int b = m / ohw, pix = m - b * ohw;
     const int64_t idx = ((int64_t)b * g.OC + n0) * ohw + pix;

@@ -34,9 +34,13 @@ struct DenseArgs : GemmCore {
   int mode;
 };
 
-template <int AMODE, int BMODE>
+// TRANSPOSE: the epilogue writes C through the warp transpose tile (whole-warp accesses
+// of one row: the read-modify-write of the SGD update); otherwise one row per thread.
+template <int AMODE, int BMODE, bool TRANSPOSE = false>
 struct DensePolicy {
   using Args = DenseArgs;
+  static constexpr bool kEpiTranspose = TRANSPOSE;
+  static constexpr int kEpiCols = 32;
   struct A : MatrixOperand<AMODE, BM, LA> {
     __device__ __forceinline__ void init(const Args &g) { this->setup(g.A, g.lda, g.M, g.K, BM); }
     __device__ __forceinline__ void tile(const Args &, int t, int) { this->set_tile(t); }
@@ -54,47 +58,68 @@ struct DensePolicy {
     else g.C[m * g.ldc + n] = acc;
   }
 
-  static __device__ __forceinline__ void store16(const Args &g, int m, int n0, const float (&v)[16],
-                                                 int nv) {
-    float *crow = g.C + (int64_t)m * g.ldc + n0;
-    if (g.epi != EPI_UPDATE && nv == 16 && (g.ldc & 3) == 0 &&
-        (reinterpret_cast<uintptr_t>(g.C) & 15) == 0) {
-      float b[16];
+  // The accumulator arrives one ROW per lane; C is row-major, so the 32 x 32 block goes
+  // through the warp's transpose tile and every global access of the warp is one
+  // contiguous 128-byte run of one row (also the read-modify-write of the SGD update).
+  static __device__ __forceinline__ void store_cols(const Args &g, int row0, int lane, int n0,
+                                                 const float (&v)[32], int nv, float *stage) {
+    if (!TRANSPOSE) {
+      const int m = row0 + lane;
+      if (m >= g.M) return;
+      float *crow = g.C + (int64_t)m * g.ldc + n0;
+      if (g.epi != EPI_UPDATE && nv == 32 && (g.ldc & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0) {
+        const float *bp = g.bias + (int64_t)n0 * g.ldbias;
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        b[j] = g.epi == EPI_BIAS ? __ldg(g.bias + (int64_t)(n0 + j) * g.ldbias) : 0.0f;
+        for (int q = 0; q < 8; ++q) {
+          float b[4] = {0.f, 0.f, 0.f, 0.f};
+          if (g.epi == EPI_BIAS) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4 *>(crow + 4 * q) =
-            make_float4(v[4 * q] + b[4 * q], v[4 * q + 1] + b[4 * q + 1],
-                        v[4 * q + 2] + b[4 * q + 2], v[4 * q + 3] + b[4 * q + 3]);
-      return;
-    }
-    if (g.epi == EPI_UPDATE) {
-      // out = W - lr*g | -lr*g | out - lr*g  (back_prop.kernel.cl:28-44 + combine)
-      const float rate = g.lr[0];
-      const float *wrow = g.Wold + (int64_t)m * g.ldc + n0;
-      if (g.mode == PB_NEW_WEIGHTS) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nv) crow[j] = wrow[j] - rate * v[j];
-      } else if (g.mode == PB_WEIGHT_DELTAS) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nv) crow[j] = -rate * v[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nv) crow[j] += -rate * v[j];
+            for (int i = 0; i < 4; ++i, bp += g.ldbias) b[i] = __ldg(bp);
+          }
+          *reinterpret_cast<float4 *>(crow + 4 * q) = make_float4(
+              v[4 * q] + b[0], v[4 * q + 1] + b[1], v[4 * q + 2] + b[2], v[4 * q + 3] + b[3]);
+        }
+        return;
       }
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nv) store1(g, m, n0 + j, v[j]);
       return;
     }
-    const float *bp = g.bias + (int64_t)n0 * g.ldbias;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < nv) crow[j] = g.epi == EPI_BIAS ? __ldg(bp) + v[j] : v[j];
-      bp += g.ldbias;
+    for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+    __syncwarp();
+    const int rows = min(32, g.M - row0);
+    const bool col_ok = lane < nv;
+    float *c = g.C + (int64_t)row0 * g.ldc + n0 + lane;
+    if (g.epi == EPI_UPDATE) {
+      const float rate = g.lr[0];
+      if (g.mode == PB_WEIGHT_DELTAS) {
+#pragma unroll 8
+        for (int r = 0; r < rows; ++r, c += g.ldc)
+          if (col_ok) *c = -rate * stage[r * 33 + lane];
+      } else {
+        // out = W - lr*g (new_weights_*) or out += -lr*g (weight_deltas_* + vector_accumulate)
+        const float *w = g.mode == PB_NEW_WEIGHTS ? g.Wold + (int64_t)row0 * g.ldc + n0 + lane : c;
+        for (int r8 = 0; r8 < rows; r8 += 8) {
+          float old[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            old[i] = (col_ok && r8 + i < rows) ? w[(int64_t)(r8 + i) * g.ldc] : 0.0f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (col_ok && r8 + i < rows)
+              c[(int64_t)(r8 + i) * g.ldc] = old[i] - rate * stage[(r8 + i) * 33 + lane];
+        }
+      }
+    } else {
+      const float b = (g.epi == EPI_BIAS && col_ok) ? __ldg(g.bias + (int64_t)(n0 + lane) * g.ldbias) : 0.0f;
+#pragma unroll 8
+      for (int r = 0; r < rows; ++r, c += g.ldc)
+        if (col_ok) *c = stage[r * 33 + lane] + b;
     }
+    __syncwarp();
   }
 };
 
@@ -154,7 +179,7 @@ int dense_weight_update_umma(pb_context *ctx, const pb_layer_desc *l, const floa
   DenseArgs g{};
   g.A = G; g.lda = nout; g.B = I; g.ldb = in; g.K = (int)batch;
   g.epi = EPI_UPDATE; g.C = out; g.ldc = in + 1; g.Wold = W; g.lr = lr; g.mode = mode;
-  if (launch_gemm<DensePolicy<OP_MN, OP_MN>>(ctx, g, (int)nout, (int)in, (int)batch)) return 1;
+  if (launch_gemm<DensePolicy<OP_MN, OP_MN, true>>(ctx, g, (int)nout, (int)in, (int)batch)) return 1;
   dense_bias_update_kernel<<<pb_div_up(nout, 128), 128, 0, ctx->stream>>>(G, W, out, lr, (int)in,
                                                                          (int)nout, batch, mode);
   PB_LAUNCHED(ctx);

@@ -61,11 +61,24 @@ struct pb_nnet {
   } pipe;
   bool alias_input = false;
   bool fuse = true;
+  pb::delta_hook_fn delta_hook = nullptr;  // data-parallel overlap, see common.cuh
+  void *delta_hook_user = nullptr;
 };
 
 namespace pb {
 
 int layer_check(const pb_layer_desc *l);
+
+void nnet_set_delta_hook(pb_nnet *net, delta_hook_fn hook, void *user) {
+  net->delta_hook = hook;
+  net->delta_hook_user = user;
+}
+
+static int fire_delta_hook(pb_nnet *net, int l, bool last_chunk) {
+  if (!net->delta_hook || !last_chunk || net->nw[l] == 0) return 0;
+  return net->delta_hook(net->delta_hook_user, l, net->deltas + net->w_off[l],
+                         net->weights + net->w_off[l], net->nw[l]);
+}
 
 __global__ void xavier_kernel(float *__restrict__ w, int64_t n, float stddev,
                               unsigned long long seed, unsigned long long base) {
@@ -152,7 +165,8 @@ static int forward_fused(pb_nnet *net, const float *d_in, int64_t batch,
 // Reverse loop over the fused plan; same per-layer order as backward().
 static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool first_chunk,
                           const std::vector<const float *> &layer_in,
-                          const std::vector<char> &fused_fwd, int top, bool in_place) {
+                          const std::vector<char> &fused_fwd, int top, bool in_place,
+                          bool last_chunk) {
   const int n = (int)net->layers.size();
   for (int l = top; l >= 0; --l) {
     const pb_layer_desc *L = &net->layers[l];
@@ -186,6 +200,7 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
       float *out = in_place ? W : net->deltas + net->w_off[l];
       if (pb_layer_weight_update(net->ctx, L, in, W, g, out, net->lr, m, batch)) return 1;
       mark(net, layer_tag(net, l) + (in_place ? ":weight_update (in place)" : ":weight_update"));
+      if (!in_place && fire_delta_hook(net, l, last_chunk)) return 1;
     }
     float *t = g; g = ng; ng = t;
   }
@@ -223,7 +238,7 @@ static int forward(pb_nnet *net, const float *d_in, int64_t batch) {
 // last layer on entry.  Per layer: input_delta with the pre-update weights,
 // then the weight kernel.  Returns the buffer holding dE/dInput in *g_out.
 static int backward(pb_nnet *net, const float *d_in, int64_t batch, float *g, float *ng,
-                    int mode, bool first_chunk, float **g_out) {
+                    int mode, bool first_chunk, float **g_out, bool last_chunk = true) {
   for (int l = (int)net->layers.size() - 1; l >= 0; --l) {
     const pb_layer_desc *L = &net->layers[l];
     const float *layer_in = (l > 0) ? net->outputs[l - 1] : d_in;
@@ -239,6 +254,7 @@ static int backward(pb_nnet *net, const float *d_in, int64_t batch, float *g, fl
                     : first_chunk            ? PB_WEIGHT_DELTAS
                                              : PB_ACCUMULATE;
       if (pb_layer_weight_update(net->ctx, L, layer_in, W, g, out, net->lr, m, batch)) return 1;
+      if (mode != PB_NEW_WEIGHTS && fire_delta_hook(net, l, last_chunk)) return 1;
     }
     float *t = g; g = ng; ng = t;
   }
@@ -577,6 +593,7 @@ static int batch_pass(pb_nnet *net, const float *d_ins, const float *d_expected,
                                      in_place ? W : net->deltas + net->w_off[h], net->lr, m, nb))
             return 1;
           pb::mark(net, pb::layer_tag(net, h) + ":weight_update");
+          if (!in_place && pb::fire_delta_hook(net, h, b0 + net->max_batch >= batch)) return 1;
           top = h - 1;
           head_done = true;
         } else {
@@ -594,7 +611,9 @@ static int batch_pass(pb_nnet *net, const float *d_ins, const float *d_expected,
           pb_error_gradients(ctx, net->loss, nout, net->outputs.back(), d_expected + b0 * nout,
                              net->grad_a, nb))
         return 1;
-      if (pb::backward_fused(net, nb, g, ng, b0 == 0, layer_in, fused_fwd, top, in_place)) return 1;
+      if (pb::backward_fused(net, nb, g, ng, b0 == 0, layer_in, fused_fwd, top, in_place,
+                             b0 + net->max_batch >= batch))
+        return 1;
       continue;
     }
     if (pb::forward(net, in, nb)) return 1;
@@ -603,7 +622,8 @@ static int batch_pass(pb_nnet *net, const float *d_ins, const float *d_expected,
       return 1;
     float *g = nullptr;
     if (pb::backward(net, in, nb, net->grad_a, net->grad_b,
-                     in_place ? PB_NEW_WEIGHTS : PB_WEIGHT_DELTAS, b0 == 0, &g))
+                     in_place ? PB_NEW_WEIGHTS : PB_WEIGHT_DELTAS, b0 == 0, &g,
+                     b0 + net->max_batch >= batch))
       return 1;
   }
   return 0;

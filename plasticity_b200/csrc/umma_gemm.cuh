@@ -30,7 +30,10 @@
 //   struct A { void init(const Args&); void tile(const Args&, int tile_m, int p);
 //              void load(const Args&, int k_stage, int p); void store(float4 *hi, int p) const; };
 //   struct B { same, with tile_n };            (p = thread index in the 128-thread group)
-//   static void store16(const Args&, int m, int n0, const float (&v)[16], int n_valid);
+//   static constexpr int kEpiCols (16 or 32); static constexpr bool kEpiTranspose;
+//   static void store_cols(const Args&, int row0, int lane, int n0, const float (&v)[kEpiCols],
+//                          int n_valid, float *stage);   (v = columns n0.. of row row0+lane;
+//                          stage = this warp's 32x33 transpose tile if kEpiTranspose)
 //   static void store1(const Args&, int64_t m, int n, float acc);     (split-K reduce)
 #pragma once
 #include "common.cuh"
@@ -43,7 +46,10 @@ namespace ugemm {
 using namespace umma;
 
 constexpr int BM = 128, BN = 256, BK = 16, STAGES = 4;
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kGroups = 3, kGroupThreads = 128;
+#ifndef PB_GEMM_GROUPS
+#define PB_GEMM_GROUPS 3
+#endif
+constexpr int kEpiWarps = 4, kMmaWarp = 4, kGroups = PB_GEMM_GROUPS, kGroupThreads = 128;
 constexpr int kThreads = (kEpiWarps + 1) * 32 + kGroups * kGroupThreads;  // 544
 // Plane pitches in 16-byte units.  = 2 (mod 8): the float4 stores of a quarter
 // warp (2 rows x 4 chunks) and the scalar stores of a warp (2 rows x 16 k) hit
@@ -51,7 +57,16 @@ constexpr int kThreads = (kEpiWarps + 1) * 32 + kGroups * kGroupThreads;  // 544
 constexpr int LA = BM + 2, LB = BN + 2;
 constexpr int CHUNKS = BK / 4;
 constexpr int STAGE_UNITS = 2 * CHUNKS * (LA + LB);  // float4 per stage
+// 194.1 KiB: stays under the 196 KiB shared-memory carve-out step, which leaves 60 KiB
+// of L1 for the operand gathers (the next step, 228 KiB, leaves 28).
 constexpr size_t kSmem = 16 * (size_t)STAGES * STAGE_UNITS + 8 * (2 * STAGES + 4) + 16;
+// Optional (policy P::kEpiTranspose): per epilogue warp a 32 x 32 transpose tile, pitch 33
+// (conflict-free both ways), for policies whose C rows must be written by whole warps.
+constexpr int kEpiStage = 32 * 33;
+template <class P>
+constexpr size_t smem_bytes() {
+  return kSmem + (P::kEpiTranspose ? 4 * (size_t)kEpiWarps * kEpiStage : 0);
+}
 
 struct GemmCore {
   int M, N;
@@ -201,14 +216,20 @@ struct MatrixOperand {
   }
 };
 
+#ifdef PB_GEMM_MAXNREG
+#define PB_GEMM_BOUNDS __maxnreg__(PB_GEMM_MAXNREG)
+#else
+#define PB_GEMM_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
 template <class P>
-__global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_constant__ typename P::Args g) {
+__global__ void PB_GEMM_BOUNDS umma_gemm_kernel(const __grid_constant__ typename P::Args g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float4 *stage_s = reinterpret_cast<float4 *>(smem_raw);  // [STAGES][STAGE_UNITS]
   uint64_t *bars = reinterpret_cast<uint64_t *>(stage_s + STAGES * STAGE_UNITS);
   uint64_t *full = bars, *empty = bars + STAGES, *d_full = bars + 2 * STAGES,
            *d_empty = bars + 2 * STAGES + 2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+  float *epi_stage = reinterpret_cast<float *>(tmem_ptr + 4);  // [kEpiWarps][kEpiStage]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -319,24 +340,27 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       const int acc = tc & 1;
       mbar_wait(&d_full[acc], (tc >> 1) & 1);
       tc_fence_after();
-      const int m = tm * BM + warp * 32 + lane;
-      const bool m_ok = m < g.M;
+      const int row0 = tm * BM + warp * 32;
+      const int m = row0 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
       const int n_lim = min(BN, g.N - tn * BN);
+      constexpr int EC = P::kEpiCols;  // accumulator columns per epilogue step: 16 or 32
 #pragma unroll 1
-      for (int c0 = 0; c0 < n_lim; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (!m_ok) continue;
-        const int n0 = tn * BN + c0, nv = min(16, n_lim - c0);
-        if (g.splits > 1) {
-          float *dst = g.partial + ((int64_t)sp * g.M + m) * g.N + n0;
+      for (int c0 = 0; c0 < n_lim; c0 += EC) {
+        float v[EC];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nv) dst[j] = v[j];
+        for (int q = 0; q < EC / 16; ++q) tmem_ld16(taddr + c0 + 16 * q, v + 16 * q);
+        tmem_ld_wait();
+        const int n0 = tn * BN + c0, nv = min(EC, n_lim - c0);
+        if (g.splits > 1) {
+          if (m < g.M) {
+            float *dst = g.partial + ((int64_t)sp * g.M + m) * g.N + n0;
+#pragma unroll
+            for (int j = 0; j < EC; ++j)
+              if (j < nv) dst[j] = v[j];
+          }
         } else {
-          P::store16(g, m, n0, v, nv);
+          P::store_cols(g, row0, lane, n0, v, nv, epi_stage + warp * kEpiStage);
         }
       }
       tc_fence_before();
@@ -371,7 +395,8 @@ int launch_gemm(pb_context *ctx, typename P::Args g, int M, int N, int K) {
   auto kern = umma_gemm_kernel<P>;
   static bool configured = false;
   if (!configured) {
-    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_bytes<P>()));
     configured = true;
   }
   g.M = M;
@@ -392,7 +417,7 @@ int launch_gemm(pb_context *ctx, typename P::Args g, int M, int N, int K) {
     g.partial = ctx->workspace;
   }
   const int grid = std::min(tiles * g.splits, ctx->num_sms);
-  kern<<<grid, kThreads, kSmem, ctx->stream>>>(g);
+  kern<<<grid, kThreads, smem_bytes<P>(), ctx->stream>>>(g);
   PB_LAUNCHED(ctx);
   if (g.splits > 1) {
     splitk_reduce_kernel<P><<<pb_ew_grid(ctx, (int64_t)M * N, 256), 256, 0, ctx->stream>>>(g);

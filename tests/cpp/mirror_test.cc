@@ -7,6 +7,7 @@
 #include <set>
 
 #include "nnet/nnet.h"
+#include "nnet/yolov1.h"
 
 static int failures = 0;
 #define EXPECT_NEAR(a, b, eps)                                                            \
@@ -117,7 +118,37 @@ static void SaveLoadAndBatch() {
   EXPECT_TRUE(a.WeightsToString() != saved);
 }
 
+// nnet/yolov1.{h,cc}: the repaired layer list chains at the reference's size, and a
+// scaled-down instance evaluates a batch, trains one sample and moves its outputs.
+static void Yolo() {
+  Architecture full = YoloArchitecture();
+  EXPECT_TRUE(full.VerifyArchitecture());
+  EXPECT_TRUE(full.layers.size() == 55);
+  EXPECT_TRUE(full.input_size() == 448 * 448 * 3 && full.output_size() == 1470);
+  size_t params = 0;
+  for (auto &l : full.layers) params += l.weight_buffer().size();
+  EXPECT_TRUE(params == 266721790);
+  Yolov1 yolo(/*max_batch=*/4, /*input_width=*/64, /*dense_width=*/64, /*outputs=*/30);
+  EXPECT_TRUE(yolo.SetParams(0.01));
+  std::vector<double> px(4 * 64 * 64 * 3);
+  for (size_t i = 0; i < px.size(); ++i) px[i] = (double)((i * 2654435761u) % 1000) / 1000.0;
+  auto images = yolo.net().MakeBuffer(px);
+  auto out = yolo.Evaluate(images);
+  out->MoveToCpu();
+  EXPECT_TRUE(out->size() == 4 * 30);
+  for (size_t i = 0; i < out->size(); ++i) EXPECT_TRUE(out->at(i) > 0.0 && out->at(i) < 1.0);  // sigmoid
+  std::vector<double> one(px.begin(), px.begin() + 64 * 64 * 3), target(30, 0.25);
+  auto image = yolo.net().MakeBuffer(one);
+  auto expected = yolo.net().MakeBuffer(target);
+  auto before = yolo.Evaluate(image);
+  const double e0 = yolo.net().Error(before, expected);
+  for (int k = 0; k < 5; ++k) yolo.TrainSample(image, expected);
+  auto after = yolo.Evaluate(image);
+  EXPECT_TRUE(yolo.net().Error(after, expected) < e0);
+}
+
 int main() {
+  Yolo();
   OneLayerRelu();
   MazurStep();
   ConvLayout();

@@ -1,7 +1,9 @@
 """Data-parallel parity on real GPUs (run under torchrun, one rank per GPU):
 ranks train 3 gradient-sum steps on shards of a global batch; the result must be
 bit-identical across ranks and match a single-GPU run over the whole batch.
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py"""
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py [cifar|mlp]
+cifar: 22 466 weights -> the fused NVLink peer-memory exchange; mlp (width 1200, 2.9 M
+weights) -> the per-layer NCCL all-reduce overlapped with the backward pass."""
 import ctypes as C, os, sys, zlib
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,8 +18,13 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-name = "cifar"
-spec = po.spec_text(name)
+name = sys.argv[1] if len(sys.argv) > 1 else "cifar"
+if name == "mlp":
+    Wd = 1200
+    spec = (f"loss ce\nact {Wd} identity\ndense {Wd} {Wd}\nact {Wd} sigmoid\ndense {Wd} {Wd}\n"
+            f"act {Wd} sigmoid\ndense {Wd} 10\nact 10 identity\nsoftmax 10\n")
+else:
+    spec = po.spec_text(name)
 S = po.RestatedNet(spec)
 model, loss = util.architecture_from_spec(spec)
 rng = np.random.default_rng(123)            # same stream on every rank
@@ -40,7 +47,7 @@ w = util.read_product_weights(net, S)
 allw = [torch.zeros(w.size, dtype=torch.float64, device="cuda") for _ in range(world)]
 dist.all_gather(allw, torch.tensor(w, device="cuda"))
 same = all(torch.equal(allw[0], a) for a in allw)
-msg = f"rank {rank}: ranks bit-identical={same}"
+msg = f"{name} rank {rank}: ranks bit-identical={same}"
 if rank == 0:
     ref = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=B, device=local)
     ref.SetLearningParameters(pb.Nnet.LearningParameters(lr))
