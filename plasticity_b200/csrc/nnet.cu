@@ -199,7 +199,7 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
       const int m = in_place ? PB_NEW_WEIGHTS : first_chunk ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
       float *out = in_place ? W : net->deltas + net->w_off[l];
       if (pb_layer_weight_update(net->ctx, L, in, W, g, out, net->lr, m, batch)) return 1;
-      mark(net, layer_tag(net, l) + (in_place ? ":weight_update (in place)" : ":weight_update"));
+      mark(net, layer_tag(net, l) + ":weight_update");
       if (!in_place && fire_delta_hook(net, l, last_chunk)) return 1;
     }
     float *t = g; g = ng; ng = t;

@@ -106,6 +106,30 @@ def main():
         if traffic:
             traffic["_source"] = f"ncu --set full capture {tag} (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
             json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    # the tensor-core GEMM configurations (wide MLP, YOLOv1): full captures + bench lines
+    for kind in ("dense", "yolo"):
+        rp = os.path.join(G, f"prof_{kind}_{tag}.ncu-rep")
+        if not os.path.exists(rp):
+            continue
+        raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        idx = {h: i for i, h in enumerate(hdr)}
+        cols = [c for c in WANT + ["lts__t_sectors_srcunit_tex_op_read.sum",
+                                   "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+                                   "sm__cycles_elapsed.max"] if c in idx]
+        with open(os.path.join(P, f"{tag}_{kind}_ncu_full.csv"), "w") as f:
+            w = csv.writer(f)
+            w.writerow([f"{c} [{units[idx[c]]}]" if units[idx[c]] else c for c in cols])
+            for d in data:
+                w.writerow([d[idx[c]] for c in cols])
+    for name in (f"mlp_{tag}.json", f"yolo_{tag}.json"):
+        src = os.path.join(G, name)
+        if os.path.exists(src):
+            lines = [l for l in open(src) if l.startswith("{")]
+            if lines:
+                open(os.path.join(P, f"{tag}_{name.split('_')[0]}.json"), "w").write(lines[-1])
     for name in (f"bench_{tag}.json", f"table_{tag}.json"):
         src = os.path.join(G, name)
         if os.path.exists(src):
