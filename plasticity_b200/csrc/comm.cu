@@ -27,6 +27,10 @@
 constexpr int kMaxP2pRanks = 8;
 constexpr int64_t kMaxP2pFloats = 1 << 20;   // above this the exchange is bandwidth-bound: NCCL
 constexpr size_t kP2pHeader = 256;           // bytes reserved for the flag words
+constexpr int kMaxBuckets = 256;             // layers of a network (one exchange bucket each)
+// flag block of the large exchange, uint32 words:
+//   [bucket][phase A|B][source rank]  then  [bucket] CTA-arrival counters
+constexpr size_t kBigFlagWords = (size_t)kMaxBuckets * 2 * kMaxP2pRanks + kMaxBuckets;
 
 struct pb_comm {
   pb_context *ctx = nullptr;
@@ -44,6 +48,14 @@ struct pb_comm {
   cudaStream_t comm_stream = nullptr;
   std::vector<cudaEvent_t> events;
   size_t events_used = 0;
+  // large delta buffers over NVLink peer memory: every rank's weight and delta buffers
+  // and a flag block are mapped into every process (CUDA IPC)
+  int big_state = 0;            // 0 = not tried, 1 = ready, -1 = unavailable (NCCL path)
+  float *big_weights = nullptr; // the local buffers the mapping was made for
+  float *big_W[kMaxP2pRanks] = {nullptr}, *big_D[kMaxP2pRanks] = {nullptr};
+  uint32_t *big_flags[kMaxP2pRanks] = {nullptr};
+  uint32_t *big_local_flags = nullptr;
+  uint32_t big_epoch = 0;
 };
 
 namespace pb {
@@ -201,6 +213,209 @@ static int p2p_setup(pb_comm *c, int64_t n) {
   return 0;
 }
 
+struct BigPeers {
+  float *W[kMaxP2pRanks];
+  float *D[kMaxP2pRanks];
+  uint32_t *flags[kMaxP2pRanks];
+};
+
+__device__ __forceinline__ bool spin_until(volatile uint32_t *word, uint32_t epoch, int *timeout_flag) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((int)(*word - epoch) < 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 5000000000ull) {  // 5 s: a rank is missing; do not hang the GPU
+      *timeout_flag = 1;
+      return false;
+    }
+  }
+  return true;
+}
+
+// One bucket (= one layer's slice [off, off+n) of the flat weight / delta buffers) of the
+// data-parallel exchange, FUSED with the weight update, over NVLink peer memory:
+//   A. publish "my deltas of this bucket are complete" to every rank, wait for everyone's;
+//   B. reduce-scatter by reading: this rank owns 1/R of the bucket, loads that part of
+//      every rank's delta buffer (peer loads, summed in rank order), adds it to its weights
+//      and STORES the new weights into every rank's weight buffer (the all-gather is of the
+//      updated weights, not of the deltas): weights are bit-identical on all ranks;
+//   C. the last CTA publishes "my part is written everywhere" and waits for everyone's.
+// Small CTAs (256 threads, no shared memory) so they co-reside with the persistent GEMM
+// CTAs of the backward pass that is still running on the compute stream.
+template <int R, int U>
+__device__ __forceinline__ void bucket_reduce_apply(const BigPeers &P, int64_t off, int64_t s0,
+                                                    int64_t s1, int rank) {
+  // U positions x R ranks of independent 16-byte loads in flight per thread: peer loads
+  // cost ~2 us, the exchange is latency-bound without deep memory-level parallelism.
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = s0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < s1;
+       i0 += stride * U) {
+    float4 v[U][R], w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < s1) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[u][q] = reinterpret_cast<const float4 *>(P.D[q] + off)[i];
+        w[u] = reinterpret_cast<const float4 *>(P.W[rank] + off)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < s1) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {  // rank order: identical sums everywhere
+          acc.x += v[u][q].x; acc.y += v[u][q].y; acc.z += v[u][q].z; acc.w += v[u][q].w;
+        }
+        float4 x = w[u];
+        x.x += acc.x; x.y += acc.y; x.z += acc.z; x.w += acc.w;
+#pragma unroll
+        for (int q = 0; q < R; ++q) reinterpret_cast<float4 *>(P.W[q] + off)[i] = x;
+      }
+    }
+  }
+}
+
+// 128 threads, <= 96 registers: small enough to share an SM with a persistent GEMM CTA
+// (544 threads x 96 registers, 194 KiB of shared memory) of the backward pass.
+__global__ void __launch_bounds__(128, 5)
+p2p_bucket_kernel(BigPeers P, int64_t off, int64_t n, int bucket, int rank, int R,
+                  uint32_t epoch, int *timeout_flag) {
+  uint32_t *mine = P.flags[rank] + (size_t)bucket * 2 * kMaxP2pRanks;
+  uint32_t *counter = P.flags[rank] + (size_t)kMaxBuckets * 2 * kMaxP2pRanks + bucket;
+  if (threadIdx.x < R) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      *(volatile uint32_t *)(P.flags[threadIdx.x] + (size_t)bucket * 2 * kMaxP2pRanks + rank) = epoch;
+    }
+    spin_until(mine + threadIdx.x, epoch, timeout_flag);
+  }
+  __syncthreads();
+  const int64_t n4 = n >> 2;
+  const int64_t per = (n4 + R - 1) / R;
+  const int64_t s0 = (int64_t)rank * per, s1 = min(n4, s0 + per);
+  switch (R) {
+    case 2: bucket_reduce_apply<2, 4>(P, off, s0, s1, rank); break;
+    case 3: bucket_reduce_apply<3, 2>(P, off, s0, s1, rank); break;
+    case 4: bucket_reduce_apply<4, 2>(P, off, s0, s1, rank); break;
+    case 5: bucket_reduce_apply<5, 1>(P, off, s0, s1, rank); break;
+    case 6: bucket_reduce_apply<6, 1>(P, off, s0, s1, rank); break;
+    case 7: bucket_reduce_apply<7, 1>(P, off, s0, s1, rank); break;
+    case 8: bucket_reduce_apply<8, 1>(P, off, s0, s1, rank); break;
+    default: bucket_reduce_apply<1, 4>(P, off, s0, s1, rank); break;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(counter, 1u);
+    last = prev == gridDim.x - 1;
+    if (last) *counter = 0;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < R) {
+    __threadfence_system();
+    *(volatile uint32_t *)(P.flags[threadIdx.x] + (size_t)bucket * 2 * kMaxP2pRanks +
+                           kMaxP2pRanks + rank) = epoch;
+    spin_until(mine + kMaxP2pRanks + threadIdx.x, epoch, timeout_flag);
+  }
+}
+
+// Collective: maps every rank's weight / delta buffers and flag block into this process.
+static int big_setup(pb_comm *c, float *weights, float *deltas, int n_layers) {
+  NcclApi *api = nccl_api();
+  c->big_state = -1;
+  c->big_weights = weights;
+  if (!api || !api->AllGather || c->n_ranks > kMaxP2pRanks || n_layers > kMaxBuckets) return 0;
+  const char *off = getenv("PB_DISABLE_P2P");
+  int ok = !(off && off[0] == '1');
+  cudaStream_t st = c->ctx->stream;
+  struct Rec { int ok; int pad; cudaIpcMemHandle_t w, d, f; };
+  Rec rec;
+  memset(&rec, 0, sizeof(rec));
+  if (ok && cudaMalloc((void **)&c->big_local_flags, kBigFlagWords * 4) != cudaSuccess) ok = 0;
+  if (ok && cudaMemsetAsync(c->big_local_flags, 0, kBigFlagWords * 4, st) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&rec.w, weights) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&rec.d, deltas) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&rec.f, c->big_local_flags) != cudaSuccess) ok = 0;
+  if (!ok) cudaGetLastError();
+  if (!c->d_timeout) {
+    if (cudaMalloc((void **)&c->d_timeout, sizeof(int)) != cudaSuccess) ok = 0;
+    else cudaMemsetAsync(c->d_timeout, 0, sizeof(int), st);
+  }
+  rec.ok = ok;
+  Rec *d_recs = nullptr;
+  std::vector<Rec> recs((size_t)c->n_ranks);
+  PB_CUDA(cudaMalloc((void **)&d_recs, sizeof(Rec) * c->n_ranks));
+  PB_CUDA(cudaMemcpyAsync(d_recs + c->rank, &rec, sizeof(Rec), cudaMemcpyHostToDevice, st));
+  PB_NCCL(api, api->AllGather(d_recs + c->rank, d_recs, sizeof(Rec), ncclChar, c->comm, st));
+  PB_CUDA(cudaMemcpyAsync(recs.data(), d_recs, sizeof(Rec) * c->n_ranks, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_recs);
+  int all_ok = 1;
+  for (int r = 0; r < c->n_ranks; ++r) all_ok &= recs[r].ok;
+  if (all_ok) {
+    for (int r = 0; r < c->n_ranks; ++r) {
+      if (r == c->rank) {
+        c->big_W[r] = weights; c->big_D[r] = deltas; c->big_flags[r] = c->big_local_flags;
+        continue;
+      }
+      void *pw = nullptr, *pd = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&pw, recs[r].w, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pd, recs[r].d, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pf, recs[r].f, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        all_ok = 0;
+      }
+      c->big_W[r] = (float *)pw; c->big_D[r] = (float *)pd; c->big_flags[r] = (uint32_t *)pf;
+    }
+  }
+  int *d_flag = nullptr;
+  PB_CUDA(cudaMalloc((void **)&d_flag, sizeof(int) * c->n_ranks));
+  PB_CUDA(cudaMemcpyAsync(d_flag + c->rank, &all_ok, sizeof(int), cudaMemcpyHostToDevice, st));
+  PB_NCCL(api, api->AllGather(d_flag + c->rank, d_flag, sizeof(int), ncclChar, c->comm, st));
+  std::vector<int> flags((size_t)c->n_ranks);
+  PB_CUDA(cudaMemcpyAsync(flags.data(), d_flag, sizeof(int) * c->n_ranks, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_flag);
+  for (int r = 0; r < c->n_ranks; ++r) all_ok &= flags[r];
+  if (all_ok) c->big_state = 1;
+  return 0;
+}
+
+static cudaEvent_t next_event(pb_comm *c) {
+  if (c->events_used == c->events.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    c->events.push_back(e);
+  }
+  return c->events[c->events_used++];
+}
+
+// delta_hook_fn of the peer-memory path: bucket = layer.
+static int p2p_bucket_hook(void *user, int layer, float *d_delta, float *d_weights, int64_t n) {
+  (void)d_delta;
+  pb_comm *c = (pb_comm *)user;
+  cudaEvent_t ev = next_event(c);
+  PB_CUDA(cudaEventRecord(ev, c->ctx->stream));
+  PB_CUDA(cudaStreamWaitEvent(c->comm_stream, ev, 0));
+  BigPeers P;
+  for (int r = 0; r < kMaxP2pRanks; ++r) {
+    const int q = r < c->n_ranks ? r : c->rank;
+    P.W[r] = c->big_W[q]; P.D[r] = c->big_D[q]; P.flags[r] = c->big_flags[q];
+  }
+  const int64_t off = d_weights - c->big_weights;
+  const int64_t n4 = ((n + 3) & ~int64_t(3));  // layer blocks are padded to 4 floats
+  const int64_t per4 = ((n4 >> 2) + c->n_ranks - 1) / c->n_ranks;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(c->ctx->num_sms, (per4 + 511) / 512));
+  p2p_bucket_kernel<<<grid, 128, 0, c->comm_stream>>>(P, off, n4, layer, c->rank, c->n_ranks,
+                                                      c->big_epoch, c->d_timeout);
+  PB_LAUNCHED(c->ctx);
+  return 0;
+}
+
 __global__ void accumulate_slice_kernel(float *__restrict__ w, const float *__restrict__ d,
                                         int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -217,12 +432,7 @@ static int overlap_hook(void *user, int layer, float *d_delta, float *d_weights,
   pb_comm *c = (pb_comm *)user;
   NcclApi *api = nccl_api();
   PB_CHECK(api, "pb_nnet_batch_train_dp: NCCL unavailable");
-  if (c->events_used == c->events.size()) {
-    cudaEvent_t e;
-    PB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->events.push_back(e);
-  }
-  cudaEvent_t ev = c->events[c->events_used++];
+  cudaEvent_t ev = next_event(c);
   PB_CUDA(cudaEventRecord(ev, c->ctx->stream));
   PB_CUDA(cudaStreamWaitEvent(c->comm_stream, ev, 0));
   PB_NCCL(api, api->AllReduce(d_delta, d_delta, (size_t)n, ncclFloat, ncclSum, c->comm,
@@ -282,6 +492,15 @@ int pb_comm_destroy(pb_comm *comm) {
       cudaStreamDestroy(comm->comm_stream);
     }
     for (cudaEvent_t e : comm->events) cudaEventDestroy(e);
+    if (comm->big_state == 1) {
+      for (int r = 0; r < comm->n_ranks; ++r) {
+        if (r == comm->rank) continue;
+        if (comm->big_W[r]) cudaIpcCloseMemHandle(comm->big_W[r]);
+        if (comm->big_D[r]) cudaIpcCloseMemHandle(comm->big_D[r]);
+        if (comm->big_flags[r]) cudaIpcCloseMemHandle(comm->big_flags[r]);
+      }
+    }
+    if (comm->big_local_flags) cudaFree(comm->big_local_flags);
     if (comm->local) cudaFree(comm->local);
     if (comm->d_timeout) cudaFree(comm->d_timeout);
     api->CommDestroy(comm->comm);
@@ -320,17 +539,23 @@ int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
       PB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       PB_CUDA(cudaStreamCreateWithPriority(&comm->comm_stream, cudaStreamNonBlocking, hi));
     }
+    float *W = nullptr;
+    int32_t n_layers = 0;
+    if (pb_nnet_weights_device(net, &W) || pb_nnet_num_layers(net, &n_layers)) return 1;
+    if (comm->big_state == 0 || (comm->big_state == 1 && comm->big_weights != W)) {
+      PB_CHECK(comm->big_state == 0, "pb_nnet_batch_train_dp: one network per communicator");
+      if (pb::big_setup(comm, W, deltas, n_layers)) return 1;
+    }
     comm->events_used = 0;
-    pb::nnet_set_delta_hook(net, pb::overlap_hook, comm);
+    // peer-memory exchange fused with the update when every rank could map every rank;
+    // otherwise NCCL all-reduce + accumulate, both per layer and overlapped with backward
+    const bool p2p = comm->big_state == 1;
+    if (p2p) comm->big_epoch++;
+    pb::nnet_set_delta_hook(net, p2p ? pb::p2p_bucket_hook : pb::overlap_hook, comm);
     const int rc = pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch);
     pb::nnet_set_delta_hook(net, nullptr, nullptr);
     if (rc) return 1;
-    if (comm->events_used == comm->events.size()) {
-      cudaEvent_t e;
-      PB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      comm->events.push_back(e);
-    }
-    cudaEvent_t done = comm->events[comm->events_used++];
+    cudaEvent_t done = pb::next_event(comm);
     PB_CUDA(cudaEventRecord(done, comm->comm_stream));
     PB_CUDA(cudaStreamWaitEvent(comm->ctx->stream, done, 0));
     return 0;
