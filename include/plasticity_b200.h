@@ -262,6 +262,20 @@ int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
 int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
                              const float *h_expected, int64_t local_batch, float *h_outputs);
 
+/* Labelled byte records (the CIFAR-10 binary format of nnet/cifar_test.cc:191-205: one
+ * label byte + sample_size pixel bytes) decoded on the device into network inputs
+ * (signed-char pixels / their L2 norm, Sample::NormalizedInput, cifar_test.cc:66-81) and
+ * one-hot targets (Sample::OneHotEncodedOutput, :83-97).  Bit-identical to normalising in
+ * double on the host and converting to float. */
+int pb_records_decode(pb_context *ctx, const uint8_t *d_records, float *d_inputs,
+                      float *d_expected, int64_t n_records, int64_t sample_size,
+                      int64_t n_classes);
+/* pb_nnet_batch_train_host fed with such records from pinned host memory: the data set
+ * crosses PCIe as bytes (sample_size + 1 per sample) and is decoded where it is consumed.
+ * sample_size = the network's input size, n_classes = its output size. */
+int pb_nnet_batch_train_host_records(pb_nnet *net, pb_comm *comm, const uint8_t *h_records,
+                                     int64_t local_batch, float *h_outputs);
+
 /* One pb_nnet_batch_train step with a CUDA event after every kernel group; writes
  * "label<TAB>milliseconds<NL>" lines (the kernels the step really runs: fused
  * convolution blocks, the fused head, ...) into `out`.  Measurement only. */

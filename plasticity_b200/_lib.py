@@ -90,6 +90,8 @@ SIGNATURES = {
     "pb_comm_allreduce_sum": [_vp, _vp, C.c_int64],
     "pb_nnet_batch_train_dp": [_vp, _vp, _vp, _vp, C.c_int64],
     "pb_nnet_batch_train_host": [_vp, _vp, _vp, _vp, C.c_int64, _vp],
+    "pb_records_decode": [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64],
+    "pb_nnet_batch_train_host_records": [_vp, _vp, _vp, C.c_int64, _vp],
     "pb_nnet_profile_step": [_vp, _vp, _vp, C.c_int64, C.c_char_p, C.c_size_t],
     "pb_nnet_profile_evaluate": [_vp, _vp, C.c_int64, C.c_char_p, C.c_size_t],
     "pb_measure_fp32_tflops": [_vp, C.POINTER(C.c_double)],

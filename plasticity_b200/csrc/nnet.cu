@@ -55,6 +55,7 @@ struct pb_nnet {
   struct HostPipe {
     cudaStream_t copy = nullptr;
     float *x[2] = {nullptr, nullptr}, *e[2] = {nullptr, nullptr};
+    uint8_t *rec[2] = {nullptr, nullptr};  // raw byte records (pb_nnet_batch_train_host_records)
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
     int64_t cap = 0;
     uint64_t calls = 0;
@@ -383,7 +384,7 @@ int pb_nnet_destroy(pb_nnet *net) {
   if (net->pipe.copy) {
     cudaStreamSynchronize(net->pipe.copy);
     for (int i = 0; i < 2; ++i) {
-      cudaFree(net->pipe.x[i]); cudaFree(net->pipe.e[i]);
+      cudaFree(net->pipe.x[i]); cudaFree(net->pipe.e[i]); cudaFree(net->pipe.rec[i]);
       cudaEventDestroy(net->pipe.copied[i]); cudaEventDestroy(net->pipe.consumed[i]);
     }
     cudaStreamDestroy(net->pipe.copy);
@@ -694,9 +695,11 @@ int pb_nnet_batch_train(pb_nnet *net, const float *d_ins, const float *d_expecte
   return pb_nnet_apply_deltas(net);
 }
 
-int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
-                             const float *h_expected, int64_t batch, float *h_outputs) {
-  PB_CHECK(net && h_ins && h_expected, "pb_nnet_batch_train_host: null");
+// Shared body of the host-fed steps.  h_records != nullptr: byte records, decoded on the
+// device into the staging slot; otherwise fp32 inputs and targets.
+static int batch_train_host_impl(pb_nnet *net, pb_comm *comm, const float *h_ins,
+                                 const float *h_expected, const uint8_t *h_records,
+                                 int64_t batch, float *h_outputs) {
   PB_CHECK(batch >= 1 && batch <= net->max_batch,
            "pb_nnet_batch_train_host: batch exceeds the max_batch the network was created with");
   pb_context *ctx = net->ctx;
@@ -714,14 +717,22 @@ int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
     }
   }
   const int s = (int)(p.calls & 1);
+  if (h_records && !p.rec[s])
+    PB_CUDA(cudaMalloc((void **)&p.rec[s], (size_t)(p.cap * (nin + 1))));
   // slot s was last read by the step two calls ago
   if (p.calls >= 2) PB_CUDA(cudaStreamWaitEvent(p.copy, p.consumed[s], 0));
-  PB_CUDA(cudaMemcpyAsync(p.x[s], h_ins, sizeof(float) * (size_t)(batch * nin),
-                          cudaMemcpyHostToDevice, p.copy));
-  PB_CUDA(cudaMemcpyAsync(p.e[s], h_expected, sizeof(float) * (size_t)(batch * nout),
-                          cudaMemcpyHostToDevice, p.copy));
+  if (h_records) {
+    PB_CUDA(cudaMemcpyAsync(p.rec[s], h_records, (size_t)(batch * (nin + 1)),
+                            cudaMemcpyHostToDevice, p.copy));
+  } else {
+    PB_CUDA(cudaMemcpyAsync(p.x[s], h_ins, sizeof(float) * (size_t)(batch * nin),
+                            cudaMemcpyHostToDevice, p.copy));
+    PB_CUDA(cudaMemcpyAsync(p.e[s], h_expected, sizeof(float) * (size_t)(batch * nout),
+                            cudaMemcpyHostToDevice, p.copy));
+  }
   PB_CUDA(cudaEventRecord(p.copied[s], p.copy));
   PB_CUDA(cudaStreamWaitEvent(ctx->stream, p.copied[s], 0));
+  if (h_records && pb_records_decode(ctx, p.rec[s], p.x[s], p.e[s], batch, nin, nout)) return 1;
   if (comm ? pb_nnet_batch_train_dp(net, comm, p.x[s], p.e[s], batch)
            : pb_nnet_batch_train(net, p.x[s], p.e[s], batch))
     return 1;
@@ -731,6 +742,18 @@ int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
                             cudaMemcpyDeviceToHost, ctx->stream));
   p.calls++;
   return 0;
+}
+
+int pb_nnet_batch_train_host(pb_nnet *net, pb_comm *comm, const float *h_ins,
+                             const float *h_expected, int64_t batch, float *h_outputs) {
+  PB_CHECK(net && h_ins && h_expected, "pb_nnet_batch_train_host: null");
+  return batch_train_host_impl(net, comm, h_ins, h_expected, nullptr, batch, h_outputs);
+}
+
+int pb_nnet_batch_train_host_records(pb_nnet *net, pb_comm *comm, const uint8_t *h_records,
+                                     int64_t batch, float *h_outputs) {
+  PB_CHECK(net && h_records, "pb_nnet_batch_train_host_records: null");
+  return batch_train_host_impl(net, comm, nullptr, nullptr, h_records, batch, h_outputs);
 }
 
 }  // extern "C"

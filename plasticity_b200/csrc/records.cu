@@ -1,0 +1,63 @@
+// Device-side decoding of labelled byte records — the CIFAR-10 binary format read by
+// nnet/cifar_test.cc:191-205: one label byte followed by `sample_size` pixel bytes —
+// into what the network trains on:
+//   input   x[i] = (double)(signed char)pixel[i] / ||pixels||_2   (norm 0 -> 1),
+//           Sample::NormalizedInput, cifar_test.cc:66-81 (the reference reads the bytes
+//           as signed `char`, :55-62)
+//   target  one-hot of the label, Sample::OneHotEncodedOutput, cifar_test.cc:83-97
+// so that a host-resident data set crosses PCIe as bytes (3 073 B per image instead of
+// 12 328 B of fp32) and is normalised where it is consumed.  The sum of squares is exact
+// (integers), the quotient is formed in double and rounded to fp32 once: bit-identical to
+// normalising in double on the host and converting to float.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace pb {
+
+// One CTA per record.
+__global__ void __launch_bounds__(256)
+decode_records_kernel(const uint8_t *__restrict__ rec, float *__restrict__ x,
+                      float *__restrict__ e, int sample_size, int n_classes) {
+  __shared__ unsigned long long red[8];
+  __shared__ double inv_s;
+  const uint8_t *r = rec + (int64_t)blockIdx.x * (sample_size + 1);
+  const signed char *px = reinterpret_cast<const signed char *>(r + 1);
+  unsigned long long sum = 0;
+  for (int i = threadIdx.x; i < sample_size; i += blockDim.x) {
+    const int v = px[i];
+    sum += (unsigned long long)(v * v);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    double norm = sqrt((double)t);
+    if (norm == 0) norm = 1;
+    inv_s = norm;
+  }
+  __syncthreads();
+  const double norm = inv_s;
+  float *xo = x + (int64_t)blockIdx.x * sample_size;
+  for (int i = threadIdx.x; i < sample_size; i += blockDim.x) xo[i] = (float)((double)px[i] / norm);
+  const int label = r[0];
+  float *eo = e + (int64_t)blockIdx.x * n_classes;
+  for (int i = threadIdx.x; i < n_classes; i += blockDim.x) eo[i] = i == label ? 1.0f : 0.0f;
+}
+
+}  // namespace pb
+
+extern "C" int pb_records_decode(pb_context *ctx, const uint8_t *d_records, float *d_inputs,
+                                 float *d_expected, int64_t n_records, int64_t sample_size,
+                                 int64_t n_classes) {
+  PB_CHECK(ctx && d_records && d_inputs && d_expected, "pb_records_decode: null");
+  PB_CHECK(n_records >= 0 && sample_size >= 1 && n_classes >= 1 && n_records < (1ll << 31) &&
+               sample_size < (1ll << 31) && n_classes < (1ll << 31),
+           "pb_records_decode: bad sizes");
+  if (n_records == 0) return 0;
+  pb::decode_records_kernel<<<(unsigned)n_records, 256, 0, ctx->stream>>>(
+      d_records, d_inputs, d_expected, (int)sample_size, (int)n_classes);
+  PB_LAUNCHED(ctx);
+  return 0;
+}

@@ -501,6 +501,14 @@ class Nnet:
         L.call("pb_nnet_batch_train_host", self.h, comm, h_inputs, h_expected, batch, h_outputs)
         self._dev_dirty = [n > 0 for n in self.nw]
 
+    def BatchTrainHostRecords(self, h_records, batch: int, h_outputs=None, comm=None) -> None:
+        """BatchTrainHost over labelled byte records (1 label byte + input_size pixel
+        bytes each, the CIFAR-10 binary format) in pinned host memory; normalisation and
+        one-hot encoding happen on the device (cifar_test.cc:66-97)."""
+        self._sync_to_device()
+        L.call("pb_nnet_batch_train_host_records", self.h, comm, h_records, batch, h_outputs)
+        self._dev_dirty = [n > 0 for n in self.nw]
+
     def Finish(self) -> None:
         L.call("pb_context_finish", self.ctx)
 

@@ -333,3 +333,67 @@ def test_batch_train_host_pipeline_matches_device_path(ctx):
         np.testing.assert_allclose(got[t], outs_dev[t], rtol=1e-5, atol=1e-7)
     for p in (hx, he, ho):
         L.call("pb_host_free", p)
+
+
+def test_records_decode_and_record_fed_training(ctx):
+    """pb_records_decode (CIFAR binary records -> L2-normalised inputs + one-hot targets,
+    cifar_test.cc:66-97) is bit-identical to normalising in double on the host and rounding
+    to fp32 — including an all-zero image (norm 0 -> 1) — and pb_nnet_batch_train_host_records
+    leaves exactly the weights the fp32-fed host pipeline leaves."""
+    name = "cifar"
+    spec = po.spec_text(name)
+    S = po.RestatedNet(spec)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(2024)
+    B, steps = 40, 3
+    px = rng.integers(-128, 128, size=(steps, B, S.n_in)).astype(np.int8)
+    px[0, 3] = 0  # norm == 0
+    lab = rng.integers(0, 10, size=(steps, B)).astype(np.uint8)
+    rec = np.concatenate([lab[..., None], px.view(np.uint8)], axis=2)  # label byte + pixels
+    norm = np.sqrt((px.astype(np.float64) ** 2).sum(axis=2, keepdims=True))
+    norm[norm == 0] = 1.0
+    x = (px.astype(np.float64) / norm).astype(np.float32)
+    e = np.zeros((steps, B, 10), dtype=np.float32)
+    for t in range(steps):
+        e[t, np.arange(B), lab[t]] = 1.0
+    # decode on the device
+    d_rec, d_x, d_e = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    L.call("pb_buffer_alloc", ctx, (rec[0].size + 3) // 4, C.byref(d_rec))
+    L.call("pb_buffer_alloc", ctx, B * S.n_in, C.byref(d_x))
+    L.call("pb_buffer_alloc", ctx, B * 10, C.byref(d_e))
+    raw = np.zeros(((rec[0].size + 3) // 4) * 4, dtype=np.uint8)
+    raw[:rec[0].size] = rec[0].reshape(-1)
+    L.call("pb_buffer_write_f32", ctx, d_rec, raw.ctypes.data, raw.size // 4)
+    L.call("pb_records_decode", ctx, d_rec, d_x, d_e, B, S.n_in, 10)
+    gx, ge = np.empty(B * S.n_in, dtype=np.float32), np.empty(B * 10, dtype=np.float32)
+    L.call("pb_buffer_read_f32", ctx, d_x, gx.ctypes.data, gx.size)
+    L.call("pb_buffer_read_f32", ctx, d_e, ge.ctypes.data, ge.size)
+    assert np.array_equal(gx.reshape(B, -1), x[0])
+    assert np.array_equal(ge.reshape(B, -1), e[0])
+    for p in (d_rec, d_x, d_e):
+        L.call("pb_buffer_free", ctx, p)
+    # record-fed training == fp32-fed training
+    w0 = util.xavier_like(S, rng)
+    nets = []
+    for _ in range(2):
+        net = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=B)
+        net.SetLearningParameters(pb.Nnet.LearningParameters(0.01))
+        util.load_product_weights(net, S, w0)
+        nets.append(net)
+    hx, he, hr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    L.call("pb_host_alloc", x.nbytes, C.byref(hx))
+    L.call("pb_host_alloc", e.nbytes, C.byref(he))
+    L.call("pb_host_alloc", rec.nbytes, C.byref(hr))
+    C.memmove(hx, x.ctypes.data, x.nbytes)
+    C.memmove(he, e.ctypes.data, e.nbytes)
+    rec_c = np.ascontiguousarray(rec)
+    C.memmove(hr, rec_c.ctypes.data, rec_c.nbytes)
+    for t in range(steps):
+        nets[0].BatchTrainHost(C.c_void_p(hx.value + t * B * S.n_in * 4),
+                               C.c_void_p(he.value + t * B * 10 * 4), B)
+        nets[1].BatchTrainHostRecords(C.c_void_p(hr.value + t * B * (S.n_in + 1)), B)
+    nets[0].Finish()
+    nets[1].Finish()
+    assert np.array_equal(util.read_product_weights(nets[0], S), util.read_product_weights(nets[1], S))
+    for p in (hx, he, hr):
+        L.call("pb_host_free", p)
