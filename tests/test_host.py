@@ -171,3 +171,37 @@ def test_data_parallel_gradient_sum_world2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r}:\n{o}"
         assert f"rank {r} ok" in o
+
+
+def test_yolov1_architecture_is_the_repaired_reference_layer_list():
+    """nnet/yolov1.cc:7-231 with the three repairs of SURVEY 8(d): the layer list chains,
+    and its totals are the ones the survey pins for configuration 5."""
+    from plasticity_b200 import yolov1
+    m = yolov1.YoloArchitecture()
+    assert m.VerifyArchitecture()
+    assert len(m.layers) == 55
+    assert m.input_size() == 448 * 448 * 3 and m.output_size() == 7 * 7 * 30
+    convs = [l for l in m.layers if l.desc.kind == _lib.PB_CONVOLUTION]
+    pools = [l for l in m.layers if l.desc.kind == _lib.PB_MAX_POOL]
+    dense = [l for l in m.layers if l.desc.kind == _lib.PB_DENSE]
+    assert (len(convs), len(pools), len(dense)) == (23, 4, 2)
+    assert sum(l.weights.size for l in m.layers) == 266721790
+    macs = sum(l.num_outputs * l.desc.filter_width * l.desc.filter_height * l.desc.filter_depth
+               for l in convs) + sum(l.num_inputs * l.num_outputs for l in dense)
+    assert macs == 16534396928  # 33.07 GFLOP forward per image
+    assert max(l.num_outputs for l in m.layers) == 3211264
+    # repair 1: conv 2 keeps 112x112 (padding 1); repair 2: depth chains through the
+    # second 14x14 pair; repair 3: the model ends at the 1470-wide dense layer
+    assert (convs[1].desc.padding, convs[1].num_outputs) == (1, 112 * 112 * 192)
+    assert [c.desc.depth for c in convs[15:19]] == [512, 512, 1024, 512]
+    assert dense[0].desc.in_ == 7 * 7 * 1024 and dense[1].desc.out == 1470
+    # every convolution is followed by LeakyRelu, every dense layer by Sigmoid (builder defaults)
+    for i, l in enumerate(m.layers[:-1]):
+        if l.desc.kind == _lib.PB_CONVOLUTION:
+            assert m.layers[i + 1].desc.activation == pb.LeakyRelu
+        if l.desc.kind == _lib.PB_DENSE:
+            assert m.layers[i + 1].desc.activation == pb.Sigmoid
+    small = yolov1.YoloArchitecture(64, 128, 30)
+    assert small.VerifyArchitecture() and small.output_size() == 30
+    with pytest.raises(ValueError):
+        yolov1.YoloArchitecture(100)
