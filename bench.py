@@ -396,27 +396,40 @@ def run_ours(args):
         bf16_peak = peaks.get("bf16_tflops", 1590.0)
         top = rows[0]
 
+        mma_off = os.environ.get("PB_WGRAD_MMA") == "0" or os.environ.get("PB_DISABLE_UMMA") == "1"
+
         def roofline_of(r):
-            tensor = "tcgen05" in r["kernel"] or (r["kernel"].startswith("convolution") and
-                                                  r["kernel"].endswith(":input_delta"))
-            if r["flop"] > 0 and not tensor:
+            # which pipe the kernel group runs on: tcgen05 (fused conv forward, conv
+            # input-gradient), mma.sync (weight gradient of conv layers 4 and 7), FP32 FFMA
+            # (weight gradient of conv layer 1, dense layers), or none (elementwise: HBM)
+            k = r["kernel"]
+            tcgen05 = "tcgen05" in k or (k.startswith("convolution") and k.endswith(":input_delta"))
+            mma_sync = (not mma_off and k in ("convolution_layer_4:weight_update",
+                                              "convolution_layer_7:weight_update"))
+            tensor_peak = bf16_peak / 2 / 3
+            if r["flop"] > 0 and not (tcgen05 or mma_sync):
                 out = {"bound": "fp32", "peak": tf.value, "unit": "TFLOP/s",
                        "peak_source": "FP32 FFMA micro-benchmark in this run (pb_measure_fp32_tflops; "
                                       f"nominal {NOMINAL_FP32_TFLOPS:.1f}); MEASURED_PEAKS.json has no "
-                                      "FP32 entry. The weight gradient has no tensor-core form at these "
-                                      "shapes (DESIGN.md section 3)"}
+                                      "FP32 entry"}
             elif r["flop"] > 0:
-                out = {"bound": "tensor", "peak": bf16_peak, "unit": "TFLOP/s",
+                out = {"bound": "tensor", "peak": tensor_peak, "unit": "TFLOP/s",
                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else
-                                       "fallback 1590") + "; the kernel is 3xTF32 (TF32 dense peak is "
-                                       "half the bf16 figure, and every product costs 2 MMA passes), "
-                                       "bounded by shared-memory operand fetch at N<=48"}
+                                       "fallback 1590") + " / 2 (TF32 runs at half the bf16 rate) / 3 "
+                                       "(3xTF32: three MMAs per fp32 product); achieved counts "
+                                       "algorithmic fp32 FLOPs",
+                       "pipe": "mma.sync.m16n8k8 tf32 (warp-level; measured peak 278 TFLOP/s of tf32 "
+                               "MMA work = 92.7 fp32-equivalent, tools/mma_sync_probe.cu)" if mma_sync
+                               else "tcgen05.mma kind::tf32, operands from shared memory (N <= 48: "
+                                    "bounded by operand fetch, DESIGN.md 3.2)"}
             else:
                 out = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
             out["kernel"] = r["kernel"]
             out["achieved"] = r["flop"] / (r["ms"] * 1e-3) / 1e12 if r["flop"] > 0 else None
             out["frac"] = out["achieved"] / out["peak"] if out["achieved"] else None
+            if out["achieved"]:
+                out["vs_fp32_ffma_peak"] = out["achieved"] / tf.value
             out["ms"] = r["ms"]
             out["share_of_step"] = r["ms"] / total_prof
             out["traffic"] = traffic.get(r["kernel"])

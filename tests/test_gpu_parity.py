@@ -397,3 +397,41 @@ def test_records_decode_and_record_fed_training(ctx):
     assert np.array_equal(util.read_product_weights(nets[0], S), util.read_product_weights(nets[1], S))
     for p in (hx, he, hr):
         L.call("pb_host_free", p)
+
+
+@pytest.mark.parametrize("layer", [4, 7])
+@pytest.mark.parametrize("batch", [64, 301])
+def test_conv_weight_gradient_tensor_core_large_batch(ctx, layer, batch):
+    """The mma.sync 3xTF32 weight-gradient kernel (csrc/conv_wgrad_mma.cu) walks several
+    samples per CTA with per-warp register accumulators and per-(CTA, row band) partials;
+    all three update modes against the oracle's gradient sum over the whole batch."""
+    name = "cifar"
+    spec = po.spec_text(name)
+    S = po.RestatedNet(spec)
+    R = checker(name)
+    model, _ = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(77 * layer + batch)
+    w_all = util.xavier_like(S, rng)
+    desc = model.layers[layer].desc
+    ni, no, nw = S.ni[layer], S.no[layer], S.nw[layer]
+    I = util.f32(rng.normal(0, 1, (batch, ni)))
+    G = util.f32(rng.normal(0, 1, (batch, no)))
+    W = S.layer_weights(w_all, layer).copy()
+    lr = 0.01
+    dI_, dW_, dG, d_lr = Dev(ctx, I), Dev(ctx, W), Dev(ctx, G), Dev(ctx, [lr])
+    delta = np.zeros(nw)
+    for b in range(batch):
+        delta += R.weight_update(layer, I[b].copy(), W, G[b].copy(), lr, 1)
+    for mode, want in ((L.PB_NEW_WEIGHTS, W + delta), (L.PB_WEIGHT_DELTAS, delta)):
+        dOut = Dev(ctx, np.zeros(nw))
+        L.call("pb_layer_weight_update", ctx, C.byref(desc), dI_.p, dW_.p, dG.p, dOut.p, d_lr.p,
+               mode, batch)
+        util.assert_close(dOut.host(), want, f"layer {layer} weight mode {mode}")
+    dOut = Dev(ctx, np.ones(nw))
+    L.call("pb_layer_weight_update", ctx, C.byref(desc), dI_.p, dW_.p, dG.p, dOut.p, d_lr.p,
+           L.PB_ACCUMULATE, batch)
+    util.assert_close(dOut.host(), 1.0 + delta, f"layer {layer} accumulate")
+    # in place (the fused BatchTrain path): out aliases W
+    L.call("pb_layer_weight_update", ctx, C.byref(desc), dI_.p, dW_.p, dG.p, dW_.p, d_lr.p,
+           L.PB_NEW_WEIGHTS, batch)
+    util.assert_close(dW_.host(), W + delta, f"layer {layer} in place")
