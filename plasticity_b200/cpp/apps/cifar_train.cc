@@ -134,7 +134,12 @@ int main(int argc, char *argv[]) {
     else if (arg == "--synthetic") value(&synthetic);
     else if (arg == "--examples") value(&examples);
     else if (arg == "--lr" && i + 1 < argc) learning_rate = std::strtod(argv[++i], nullptr);
-    else if (arg == "--seed") { size_t s = 1; value(&s); seed = s; }
+    else if (arg == "--seed") {  // synthetic records AND the Xavier draw (PLASTICITY_SEED)
+      size_t s = 1;
+      value(&s);
+      seed = s;
+      setenv("PLASTICITY_SEED", std::to_string(s).c_str(), 1);
+    }
     else if (arg.rfind("--", 0) != 0) weight_file_path = arg;
   }
   if (only_one_epoch) epochs = 0;  // cifar_test.cc:262-264

@@ -402,8 +402,14 @@ class Nnet {
       default: {
         // Layer::XavierInitializeWeights, layer.cc:86-100: N(0, 1/num_inputs),
         // seeded from random_device like stats/normal.h:11,37.
-        std::random_device rd;
-        const uint64_t seed = ((uint64_t)rd() << 32) ^ rd();
+        // PLASTICITY_SEED=<n> in the environment makes the draw reproducible.
+        uint64_t seed;
+        if (const char *fixed = std::getenv("PLASTICITY_SEED")) {
+          seed = std::strtoull(fixed, nullptr, 10);
+        } else {
+          std::random_device rd;
+          seed = ((uint64_t)rd() << 32) ^ rd();
+        }
         PB_CHECK_OK(pb_nnet_init_xavier(net_, seed));
         host_dirty_.assign(model_.layers.size(), false);
         MarkDeviceNewer();
