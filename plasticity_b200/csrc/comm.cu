@@ -529,11 +529,17 @@ int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
     const char *e = getenv("PB_DP_OVERLAP");
     return !(e && e[0] == '0');
   }();
-  if (comm->n_ranks > 1 && n > kMaxP2pFloats && overlap) {
-    // Bandwidth-bound exchange (the 4096-wide MLP: 134 MB): one all-reduce per layer,
-    // started as soon as that layer's weight gradient is done — last layer first — on a
-    // high-priority second stream, so the transfer of layer l overlaps the backward
-    // kernels of layers l-1, l-2, ...
+  // PB_DP_BUCKETS=0: small delta buffers use the single-kernel inbox exchange after the pass
+  static const bool small_buckets = [] {
+    const char *e = getenv("PB_DP_BUCKETS");
+    return !(e && e[0] == '0');
+  }();
+  if (comm->n_ranks > 1 && overlap && (n > kMaxP2pFloats || small_buckets)) {
+    // One exchange per layer, started as soon as that layer's weight gradient is done —
+    // last layer first — on a high-priority second stream, so the exchange of layer l
+    // overlaps the backward kernels of layers l-1, l-2, ...: for the bandwidth-bound case
+    // (the 4096-wide MLP: 134 MB) and for the latency-bound one (the CIFAR net: 90 KB,
+    // where only the first layer's 5 KB bucket stays exposed) alike.
     if (!comm->comm_stream) {
       int lo = 0, hi = 0;
       PB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -546,19 +552,21 @@ int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
       PB_CHECK(comm->big_state == 0, "pb_nnet_batch_train_dp: one network per communicator");
       if (pb::big_setup(comm, W, deltas, n_layers)) return 1;
     }
-    comm->events_used = 0;
     // peer-memory exchange fused with the update when every rank could map every rank;
-    // otherwise NCCL all-reduce + accumulate, both per layer and overlapped with backward
+    // otherwise NCCL all-reduce + accumulate per layer (large buffers) or the paths below
     const bool p2p = comm->big_state == 1;
-    if (p2p) comm->big_epoch++;
-    pb::nnet_set_delta_hook(net, p2p ? pb::p2p_bucket_hook : pb::overlap_hook, comm);
-    const int rc = pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch);
-    pb::nnet_set_delta_hook(net, nullptr, nullptr);
-    if (rc) return 1;
-    cudaEvent_t done = pb::next_event(comm);
-    PB_CUDA(cudaEventRecord(done, comm->comm_stream));
-    PB_CUDA(cudaStreamWaitEvent(comm->ctx->stream, done, 0));
-    return 0;
+    if (p2p || n > kMaxP2pFloats) {
+      comm->events_used = 0;
+      if (p2p) comm->big_epoch++;
+      pb::nnet_set_delta_hook(net, p2p ? pb::p2p_bucket_hook : pb::overlap_hook, comm);
+      const int rc = pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch);
+      pb::nnet_set_delta_hook(net, nullptr, nullptr);
+      if (rc) return 1;
+      cudaEvent_t done = pb::next_event(comm);
+      PB_CUDA(cudaEventRecord(done, comm->comm_stream));
+      PB_CUDA(cudaStreamWaitEvent(comm->ctx->stream, done, 0));
+      return 0;
+    }
   }
   if (pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch)) return 1;
   if (comm->n_ranks > 1 && n <= kMaxP2pFloats) {
