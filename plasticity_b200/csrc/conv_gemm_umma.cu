@@ -34,13 +34,18 @@ struct ConvArgs : GemmCore {
   int C, H, W, OC, OH, OW, FH, FW, stride, pad;
   int ICP;            // channels per tap in K order: 4, 8 or a multiple of 16
   int taps, Kp;
-  uint16_t tap_yx[kMaxTaps];  // tap -> (fy << 8 | fx)
+  // K order.  0: k' = tap*ICP + ic (tap_yx[tap] = fy << 8 | fx).  1 ("rows", few input
+  // channels and a wide filter — the RGB 7x7 layer): k' = (fy*C + ic)*8 + fx, one filter
+  // ROW of one channel per 8 k values (tap_yx[fy*C + ic] = fy << 8 | ic): a thread reads 8
+  // consecutive input floats per row instead of gathering taps one by one.
+  int korder;
+  uint16_t tap_yx[kMaxTaps];
 };
 
 // Wk[oc][tap*ICP + ic] = Wref[oc][ic][tap], zero in the padding.
 __global__ void retile_filters_kernel(const float *__restrict__ Wref, float *__restrict__ Wk,
                                       float *__restrict__ bias, int OC, int C, int taps, int ICP,
-                                      int Kp) {
+                                      int Kp, int korder, int FW) {
   const int64_t total = (int64_t)OC * Kp;
   const int64_t kref1 = (int64_t)C * taps + 1;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < OC;
@@ -50,6 +55,12 @@ __global__ void retile_filters_kernel(const float *__restrict__ Wref, float *__r
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t oc = t / Kp;
     const int k = (int)(t - oc * Kp);
+    if (korder == 1) {
+      const int row = k >> 3, fx = k & 7;     // row = fy*C + ic
+      const int fy = row / C, ic = row - fy * C;
+      Wk[t] = (fy * FW < taps && fx < FW) ? Wref[oc * kref1 + (int64_t)ic * taps + fy * FW + fx] : 0.0f;
+      continue;
+    }
     const int tap = k / ICP, ic = k - tap * ICP;
     Wk[t] = (tap < taps && ic < C) ? Wref[oc * kref1 + (int64_t)ic * taps + tap] : 0.0f;
   }
@@ -80,7 +91,27 @@ struct ConvPolicy {
     }
     __device__ __forceinline__ void load(const Args &g, int ks, int) {
       const int64_t hw = (int64_t)g.H * g.W;
-      if (g.ICP >= 16) {
+      if (g.korder == 1) {
+        // two filter rows (fy, ic) per stage, 8 consecutive input columns each
+        const int n_rows = g.FH * g.C;
+        const bool cols_in = ix0 >= 0 && ix0 + 7 < g.W;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = 2 * ks + h;
+          const int yc = g.tap_yx[min(row, kMaxTaps - 1)];
+          const int fy = yc >> 8, ic = yc & 255;
+          const bool ok = m_ok && row < n_rows && (unsigned)(iy0 + fy) < (unsigned)g.H;
+          const float *q = g.In + base_off + (int64_t)ic * hw + fy * g.W;
+          if (ok && cols_in) {
+#pragma unroll
+            for (int fx = 0; fx < 8; ++fx) v[8 * h + fx] = fx < g.FW ? __ldg(q + fx) : 0.0f;
+          } else {
+#pragma unroll
+            for (int fx = 0; fx < 8; ++fx)
+              v[8 * h + fx] = (ok && fx < g.FW && (unsigned)(ix0 + fx) < (unsigned)g.W) ? __ldg(q + fx) : 0.0f;
+          }
+        }
+      } else if (g.ICP >= 16) {
         // one tap per stage, 16 consecutive channels
         const int per = g.ICP >> 4;
         const int tap = ks / per, icb = ks - tap * per;
@@ -197,7 +228,10 @@ int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float
   const int64_t taps = l->filter_width * l->filter_height;
   if (C > 8 && C % 16 != 0) return -1;
   const int64_t ICP = C <= 4 ? 4 : (C <= 8 ? 8 : C);
-  const int64_t K = taps * ICP;
+  // "rows" K order when it is the shorter K: few channels under a wide (<= 8) filter
+  const int korder = (l->filter_width <= 8 && l->filter_height * C <= kMaxTaps &&
+                      l->filter_height * C * 8 < taps * ICP) ? 1 : 0;
+  const int64_t K = korder == 1 ? l->filter_height * C * 8 : taps * ICP;
   const int64_t M = batch * OH * OW;
   if (M <= 0 || OC <= 0) return 0;
   // worth a tensor-core launch?  (small products are latency-bound either way)
@@ -208,12 +242,19 @@ int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float
   const size_t bias_off = ((size_t)OC * Kp + 3) & ~(size_t)3;  // keeps the bias 16-byte aligned
   if (ensure_aux(ctx, bias_off + (size_t)OC + 16)) return 1;
   retile_filters_kernel<<<pb_ew_grid(ctx, OC * Kp, 256), 256, 0, ctx->stream>>>(
-      W, ctx->aux, ctx->aux + bias_off, (int)OC, (int)C, (int)taps, (int)ICP, Kp);
+      W, ctx->aux, ctx->aux + bias_off, (int)OC, (int)C, (int)taps, (int)ICP, Kp, korder,
+      (int)l->filter_width);
   PB_LAUNCHED(ctx);
   ConvArgs g{};
   g.In = I; g.Wk = ctx->aux; g.bias = ctx->aux + bias_off; g.Out = O; g.Out2 = O2; g.act = act;
-  for (int t = 0; t < (int)taps; ++t)
-    g.tap_yx[t] = (uint16_t)(((t / l->filter_width) << 8) | (t % l->filter_width));
+  g.korder = korder;
+  if (korder == 1) {
+    for (int r = 0; r < (int)(l->filter_height * C); ++r)
+      g.tap_yx[r] = (uint16_t)(((r / C) << 8) | (r % C));
+  } else {
+    for (int t = 0; t < (int)taps; ++t)
+      g.tap_yx[t] = (uint16_t)(((t / l->filter_width) << 8) | (t % l->filter_width));
+  }
   g.C = (int)C; g.H = (int)l->height; g.W = (int)l->width; g.OC = (int)OC;
   g.OH = (int)OH; g.OW = (int)OW; g.FH = (int)l->filter_height; g.FW = (int)l->filter_width;
   g.stride = (int)l->stride; g.pad = (int)l->padding;

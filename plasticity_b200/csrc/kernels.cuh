@@ -94,6 +94,11 @@ int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *conv, int 
 int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *I,
                             const float *W, float *O, float *O2, int act, int64_t batch);
 
+// records.cu: pb_records_decode on an explicit stream.
+int records_decode_on(pb_context *ctx, cudaStream_t stream, const uint8_t *d_records,
+                      float *d_inputs, float *d_expected, int64_t n_records, int64_t sample_size,
+                      int64_t n_classes);
+
 // Output extent of a convolution, nnet/convolution_layer.cc:36-44.
 static inline int64_t conv_out_w(const pb_layer_desc *l) {
   return (l->width - l->filter_width + 2 * l->padding) / l->stride + 1;

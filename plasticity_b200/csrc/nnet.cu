@@ -724,6 +724,8 @@ static int batch_train_host_impl(pb_nnet *net, pb_comm *comm, const float *h_ins
   if (h_records) {
     PB_CUDA(cudaMemcpyAsync(p.rec[s], h_records, (size_t)(batch * (nin + 1)),
                             cudaMemcpyHostToDevice, p.copy));
+    // decoded on the copy stream, behind the copy: overlaps the previous step's compute
+    if (pb::records_decode_on(ctx, p.copy, p.rec[s], p.x[s], p.e[s], batch, nin, nout)) return 1;
   } else {
     PB_CUDA(cudaMemcpyAsync(p.x[s], h_ins, sizeof(float) * (size_t)(batch * nin),
                             cudaMemcpyHostToDevice, p.copy));
@@ -732,7 +734,6 @@ static int batch_train_host_impl(pb_nnet *net, pb_comm *comm, const float *h_ins
   }
   PB_CUDA(cudaEventRecord(p.copied[s], p.copy));
   PB_CUDA(cudaStreamWaitEvent(ctx->stream, p.copied[s], 0));
-  if (h_records && pb_records_decode(ctx, p.rec[s], p.x[s], p.e[s], batch, nin, nout)) return 1;
   if (comm ? pb_nnet_batch_train_dp(net, comm, p.x[s], p.e[s], batch)
            : pb_nnet_batch_train(net, p.x[s], p.e[s], batch))
     return 1;

@@ -48,16 +48,30 @@ decode_records_kernel(const uint8_t *__restrict__ rec, float *__restrict__ x,
 
 }  // namespace pb
 
-extern "C" int pb_records_decode(pb_context *ctx, const uint8_t *d_records, float *d_inputs,
-                                 float *d_expected, int64_t n_records, int64_t sample_size,
-                                 int64_t n_classes) {
+namespace pb {
+
+// On `stream` (the host pipeline decodes on its copy stream, right behind the H2D copy,
+// so the decode of step i+1 overlaps the compute of step i).
+int records_decode_on(pb_context *ctx, cudaStream_t stream, const uint8_t *d_records,
+                      float *d_inputs, float *d_expected, int64_t n_records, int64_t sample_size,
+                      int64_t n_classes) {
   PB_CHECK(ctx && d_records && d_inputs && d_expected, "pb_records_decode: null");
   PB_CHECK(n_records >= 0 && sample_size >= 1 && n_classes >= 1 && n_records < (1ll << 31) &&
                sample_size < (1ll << 31) && n_classes < (1ll << 31),
            "pb_records_decode: bad sizes");
   if (n_records == 0) return 0;
-  pb::decode_records_kernel<<<(unsigned)n_records, 256, 0, ctx->stream>>>(
+  decode_records_kernel<<<(unsigned)n_records, 256, 0, stream>>>(
       d_records, d_inputs, d_expected, (int)sample_size, (int)n_classes);
   PB_LAUNCHED(ctx);
   return 0;
+}
+
+}  // namespace pb
+
+extern "C" int pb_records_decode(pb_context *ctx, const uint8_t *d_records, float *d_inputs,
+                                 float *d_expected, int64_t n_records, int64_t sample_size,
+                                 int64_t n_classes) {
+  PB_CHECK(ctx, "pb_records_decode: null");
+  return pb::records_decode_on(ctx, ctx->stream, d_records, d_inputs, d_expected, n_records,
+                               sample_size, n_classes);
 }

@@ -205,3 +205,25 @@ def test_yolov1_architecture_is_the_repaired_reference_layer_list():
     assert small.VerifyArchitecture() and small.output_size() == 30
     with pytest.raises(ValueError):
         yolov1.YoloArchitecture(100)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path: generated kernels or the
+    plain-C port, all host threads) prints exactly ONE JSON line on stdout carrying the
+    contract's keys for the same metric / config as the product arm."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--steps", "1", "--warmup", "0", "--ref-sample", "16"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "cifar_cnn_train_samples_per_sec"
+    assert d["unit"] == "samples/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "cifar_cnn_batch_train"
