@@ -110,6 +110,12 @@ class Layer {
     return Dimensions{(size_t)a, (size_t)b};
   }
 
+  // nnet/layer.h:119-123, layer.cc:28-34: the OpenCL work-group sizes of the layer's
+  // three launches (outputs / weights / inputs work-items).
+  size_t eval_workgroup_size() const { return CalculateWorkgroupSize(GetDimensions().num_outputs); }
+  size_t weight_train_workgroup_size() const { return CalculateWorkgroupSize(weights_.size()); }
+  size_t bp_train_workgroup_size() const { return CalculateWorkgroupSize(GetDimensions().num_inputs); }
+
   std::string LayerSuffix() const { return type_ + "_" + std::to_string(index_); }  // layer.h:99-101
   const pb_layer_desc &desc() const { return desc_; }
   size_t layer_index() const { return index_; }

@@ -147,7 +147,25 @@ static void Yolo() {
   EXPECT_TRUE(yolo.net().Error(after, expected) < e0);
 }
 
+// nnet/layer_dimensions.cc:12-54
+static void WorkgroupSizes() {
+  EXPECT_TRUE(CalculateWorkgroupSize(0) == 1);
+  EXPECT_TRUE(CalculateWorkgroupSize(100) == 100);
+  EXPECT_TRUE(CalculateWorkgroupSize(128) == 128);
+  EXPECT_TRUE(CalculateWorkgroupSize(16384) == 32);   // one warp per group on powers of two
+  EXPECT_TRUE(CalculateWorkgroupSize(129) == 43);     // smallest divisor >= 32
+  EXPECT_TRUE(CalculateWorkgroupSize(131) == 1);      // prime
+  EXPECT_TRUE(CalculateWorkgroupSize(192) == 32);
+  EXPECT_TRUE(CalculateWorkgroupSize(2 * 97) == 1);   // 194: no divisor in [32, 97)
+  Architecture model(3072);
+  model.AddConvolutionLayer({32, 32, 3}, {5, 5, 3, 1, 2, 16});
+  EXPECT_TRUE(model.layers[1].eval_workgroup_size() == 32);           // 16384 outputs
+  EXPECT_TRUE(model.layers[1].weight_train_workgroup_size() == 32);   // 1216 = 32 * 38
+  EXPECT_TRUE(model.layers[1].bp_train_workgroup_size() == 32);       // 3072 inputs
+}
+
 int main() {
+  WorkgroupSizes();
   Yolo();
   OneLayerRelu();
   MazurStep();
