@@ -400,11 +400,12 @@ def run_ours(args):
 
         def roofline_of(r):
             # which pipe the kernel group runs on: tcgen05 (fused conv forward, conv
-            # input-gradient), mma.sync (weight gradient of conv layers 4 and 7), FP32 FFMA
-            # (weight gradient of conv layer 1, dense layers), or none (elementwise: HBM)
+            # input-gradient), mma.sync (convolution weight gradients), FP32 FFMA (dense
+            # layers), or none (elementwise: HBM)
             k = r["kernel"]
             tcgen05 = "tcgen05" in k or (k.startswith("convolution") and k.endswith(":input_delta"))
-            mma_sync = (not mma_off and k in ("convolution_layer_4:weight_update",
+            mma_sync = (not mma_off and k in ("convolution_layer_1:weight_update",
+                                              "convolution_layer_4:weight_update",
                                               "convolution_layer_7:weight_update"))
             tensor_peak = bf16_peak / 2 / 3
             if r["flop"] > 0 and not (tcgen05 or mma_sync):

@@ -288,6 +288,235 @@ int launch(pb_context *ctx, const float *I, const float *Wt, const float *G, flo
   return 0;
 }
 
+// ---------------------------------------------------------------------------------
+// Few input channels (the RGB layer: 3 channels would fill 19 % of a 16-row M tile).
+// Here the filters are the M tile and (channel, fx) is the N dimension:
+//   D[oc 16][(ic,fx) 8] += A[oc 16][pixel 8] * B[pixel 8][(ic,fx) 8]   per filter row fy
+// 3 channels x 5 taps = 15 of 16 columns used.  A (the gradient tile) does not depend on
+// the tap: its fragments are loaded once per K step and reused for the 5 filter rows; B is
+// the input tile read at a per-lane (channel plane, fx) offset.  16 warps = 16 bands of
+// output rows, each warp holds all 5 x 2 accumulator tiles.
+// ---------------------------------------------------------------------------------
+template <int IC_, int OC_, int S_>
+struct NCfg {
+  static constexpr int IC = IC_, OC = OC_, S = S_, F = 5, PADW = 2;
+  static constexpr int WARPS = 16, THREADS = WARPS * 32;
+  static constexpr int NCOL = IC * F;               // (ic, fx) columns
+  static constexpr int NT = (NCOL + 7) / 8;
+  static constexpr int SLICES = WARPS, RPS = S / SLICES;
+  static constexpr int LEFT = 4, PITCH = S + 8, ROWS = S + 2 * PADW;
+  static constexpr int PLANE = ((ROWS * PITCH + 31) / 32) * 32 + 8;  // = 8 (mod 32)
+  static constexpr int GPLANE = S * S + 4;                            // = 4 (mod 8)
+  static constexpr int IN_ELEMS = IC * PLANE, G_ELEMS = 16 * GPLANE;
+  static constexpr int STAGE = IN_ELEMS + G_ELEMS;
+  static constexpr int MAIN_ELEMS = 2 * STAGE;
+  static constexpr int K1 = F * F * IC + 1;
+  static constexpr int FRAG_ELEMS = F * NT * 4 * 32;  // [fy][nt][i][lane]
+  static constexpr int ROW = FRAG_ELEMS + 16;          // + bias sums per filter
+  static constexpr int RED_ELEMS = (SLICES / 2) * ROW;
+  static constexpr size_t SMEM =
+      sizeof(float) * (MAIN_ELEMS > RED_ELEMS ? MAIN_ELEMS : RED_ELEMS);
+  static_assert(OC <= 16 && RPS * SLICES == S && S % 8 == 0, "envelope");
+  static_assert(SMEM <= 220 * 1024, "shared memory");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+conv_wgrad_mma_rgb_kernel(const float *__restrict__ In, const float *__restrict__ G,
+                          float *__restrict__ partial, int batch, int samples_per_cta) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, slice = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < C::MAIN_ELEMS; i += C::THREADS) smem[i] = 0.0f;
+  __syncthreads();
+  const int b0 = blockIdx.x * samples_per_cta;
+  const int b1 = min(batch, b0 + samples_per_cta);
+
+  auto load = [&](int st, int b) {
+    float *in_s = smem + st * C::STAGE, *g_s = in_s + C::IN_ELEMS;
+    const float *src = In + (int64_t)b * C::IC * C::S * C::S;
+    for (int e = tid; e < C::IC * C::S * C::S / 4; e += C::THREADS) {
+      const int x4 = e % (C::S / 4), r = e / (C::S / 4);
+      const int y = r % C::S, ic = r / C::S;
+      __pipeline_memcpy_async(in_s + ic * C::PLANE + (y + C::PADW) * C::PITCH + C::LEFT + 4 * x4,
+                              src + 4 * e, 16);
+    }
+    const float *gs = G + (int64_t)b * C::OC * C::S * C::S;
+    for (int e = tid; e < C::OC * C::S * C::S / 4; e += C::THREADS) {
+      const int q = e % (C::S * C::S / 4), oc = e / (C::S * C::S / 4);
+      __pipeline_memcpy_async(g_s + oc * C::GPLANE + 4 * q, gs + 4 * e, 16);
+    }
+  };
+
+  // this lane's column n = 8nt + g of the B fragments = (channel, fx); columns past
+  // IC*F read channel IC-1 (their products land in D columns that are never stored)
+  int boff[C::NT];
+#pragma unroll
+  for (int nt = 0; nt < C::NT; ++nt) {
+    const int n = min(nt * 8 + g, C::NCOL - 1);
+    boff[nt] = (n / C::F) * C::PLANE + (n % C::F) + (C::LEFT - C::PADW) + t;
+  }
+
+  float acc[C::F][C::NT][4];
+#pragma unroll
+  for (int fy = 0; fy < C::F; ++fy)
+#pragma unroll
+    for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[fy][nt][i] = 0.0f;
+  float bias_lo = 0.0f, bias_hi = 0.0f;  // filters g and g + 8
+
+  if (b0 < b1) load(0, b0);
+  __pipeline_commit();
+  for (int b = b0; b < b1; ++b) {
+    const int st = (b - b0) & 1;
+    if (b + 1 < b1) load(st ^ 1, b + 1);
+    __pipeline_commit();
+    __pipeline_wait_prior(1);
+    __syncthreads();
+    const float *in_s = smem + st * C::STAGE, *g_s = in_s + C::IN_ELEMS;
+#pragma unroll 1
+    for (int yy = 0; yy < C::RPS; ++yy) {
+      const int y = slice * C::RPS + yy;
+#pragma unroll 1
+      for (int x0 = 0; x0 < C::S; x0 += 8) {
+        uint32_t ah[4], al[4];
+        {
+          const float *p = g_s + g * C::GPLANE + y * C::S + x0 + t;
+          const float v0 = p[0], v1 = p[8 * C::GPLANE], v2 = p[4], v3 = p[8 * C::GPLANE + 4];
+          split(v0, ah[0], al[0]);
+          split(v1, ah[1], al[1]);
+          split(v2, ah[2], al[2]);
+          split(v3, ah[3], al[3]);
+          bias_lo += v0 + v2;
+          bias_hi += v1 + v3;
+        }
+        uint32_t bh[C::F][C::NT][2], bl[C::F][C::NT][2];
+#pragma unroll
+        for (int fy = 0; fy < C::F; ++fy)
+#pragma unroll
+          for (int nt = 0; nt < C::NT; ++nt) {
+            const float *p = in_s + boff[nt] + (y + fy) * C::PITCH + x0;
+            split(p[0], bh[fy][nt][0], bl[fy][nt][0]);
+            split(p[4], bh[fy][nt][1], bl[fy][nt][1]);
+          }
+        // pass-major: consecutive MMAs on one accumulator are F*NT instructions apart
+#pragma unroll
+        for (int fy = 0; fy < C::F; ++fy)
+#pragma unroll
+          for (int nt = 0; nt < C::NT; ++nt) mma_tf32(acc[fy][nt], al, bh[fy][nt]);
+#pragma unroll
+        for (int fy = 0; fy < C::F; ++fy)
+#pragma unroll
+          for (int nt = 0; nt < C::NT; ++nt) mma_tf32(acc[fy][nt], ah, bl[fy][nt]);
+#pragma unroll
+        for (int fy = 0; fy < C::F; ++fy)
+#pragma unroll
+          for (int nt = 0; nt < C::NT; ++nt) mma_tf32(acc[fy][nt], ah, bh[fy][nt]);
+      }
+    }
+    __syncthreads();
+  }
+  __pipeline_wait_prior(0);
+
+  // lanes t = 0..3 hold disjoint pixel subsets of filters g / g + 8
+  bias_lo += __shfl_xor_sync(0xffffffffu, bias_lo, 1);
+  bias_lo += __shfl_xor_sync(0xffffffffu, bias_lo, 2);
+  bias_hi += __shfl_xor_sync(0xffffffffu, bias_hi, 1);
+  bias_hi += __shfl_xor_sync(0xffffffffu, bias_hi, 2);
+  // row bands summed in a fixed tree order through shared memory (fragment order)
+  for (int half = C::SLICES / 2; half >= 1; half >>= 1) {
+    if (slice >= half && slice < 2 * half) {
+      float *row = smem + (slice - half) * C::ROW;
+#pragma unroll
+      for (int fy = 0; fy < C::F; ++fy)
+#pragma unroll
+        for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) row[((fy * C::NT + nt) * 4 + i) * 32 + lane] = acc[fy][nt][i];
+      if (t == 0) { row[C::FRAG_ELEMS + g] = bias_lo; row[C::FRAG_ELEMS + g + 8] = bias_hi; }
+    }
+    __syncthreads();
+    if (slice < half) {
+      const float *row = smem + slice * C::ROW;
+#pragma unroll
+      for (int fy = 0; fy < C::F; ++fy)
+#pragma unroll
+        for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[fy][nt][i] += row[((fy * C::NT + nt) * 4 + i) * 32 + lane];
+      bias_lo += row[C::FRAG_ELEMS + g];
+      bias_hi += row[C::FRAG_ELEMS + g + 8];
+    }
+    __syncthreads();
+  }
+  if (slice != 0) return;
+  float *out = partial + (int64_t)blockIdx.x * C::ROW;
+#pragma unroll
+  for (int fy = 0; fy < C::F; ++fy)
+#pragma unroll
+    for (int nt = 0; nt < C::NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[((fy * C::NT + nt) * 4 + i) * 32 + lane] = acc[fy][nt][i];
+  if (t == 0) { out[C::FRAG_ELEMS + g] = bias_lo; out[C::FRAG_ELEMS + g + 8] = bias_hi; }
+}
+
+// slot i of lane (g,t): row g + 8*(i>>1) = filter, column 8nt + 2t + (i&1) = (channel, fx)
+template <class C>
+__global__ void wgrad_mma_rgb_reduce_kernel(const float *__restrict__ partial, int n_partial,
+                                            const float *Wt, float *out,
+                                            const float *__restrict__ lr, int mode) {
+  __shared__ float red[8][32];
+  const int lane_ = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int slot = blockIdx.x * 32 + lane_;
+  float part = 0.0f;
+  if (slot < C::ROW) {
+#pragma unroll 4
+    for (int p = grp; p < n_partial; p += 8) part += partial[(int64_t)p * C::ROW + slot];
+  }
+  red[grp][lane_] = part;
+  __syncthreads();
+  if (grp != 0 || slot >= C::ROW) return;
+  int w;
+  if (slot >= C::FRAG_ELEMS) {
+    const int oc = slot - C::FRAG_ELEMS;
+    if (oc >= C::OC) return;
+    w = oc * C::K1 + C::K1 - 1;
+  } else {
+    const int lane = slot & 31, i = (slot >> 5) & 3;
+    const int r = slot >> 7, nt = r % C::NT, fy = r / C::NT;
+    const int oc = (lane >> 2) + ((i & 2) ? 8 : 0);
+    const int n = nt * 8 + 2 * (lane & 3) + (i & 1);
+    if (oc >= C::OC || n >= C::NCOL) return;
+    w = oc * C::K1 + (n / C::F) * C::F * C::F + fy * C::F + (n % C::F);
+  }
+  float acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc += red[j][lane_];
+  apply_update(mode, out, Wt, w, lr[0], acc);
+}
+
+template <class C>
+int launch_rgb(pb_context *ctx, const float *I, const float *Wt, const float *G, float *out,
+               const float *lr, int mode, int batch) {
+  auto kern = conv_wgrad_mma_rgb_kernel<C>;
+  static bool configured = false;
+  if (!configured) {
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    configured = true;
+  }
+  const int n_cta = std::min(batch, ctx->num_sms);
+  const int spc = (batch + n_cta - 1) / n_cta;
+  const int grid = (batch + spc - 1) / spc;
+  if (ensure_workspace(ctx, (size_t)grid * C::ROW)) return 1;
+  kern<<<grid, C::THREADS, C::SMEM, ctx->stream>>>(I, G, ctx->workspace, batch, spc);
+  PB_LAUNCHED(ctx);
+  wgrad_mma_rgb_reduce_kernel<C><<<pb_div_up(C::ROW, 32), 256, 0, ctx->stream>>>(
+      ctx->workspace, grid, Wt, out, lr, mode);
+  PB_LAUNCHED(ctx);
+  return 0;
+}
+
 }  // namespace
 
 // Returns -1 outside the envelope (the FFMA kernels of conv_tiled.cu then run).
@@ -303,6 +532,7 @@ int conv_weight_update_mma(pb_context *ctx, const pb_layer_desc *l, const float 
   const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
   if (w == 16 && d == 16 && f == 20) return launch<WCfg<16, 20, 16>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
   if (w == 8 && d == 20 && f == 20) return launch<WCfg<20, 20, 8>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
+  if (w == 32 && d == 3 && f == 16) return launch_rgb<NCfg<3, 16, 32>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
   return -1;
 }
 

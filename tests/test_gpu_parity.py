@@ -399,10 +399,12 @@ def test_records_decode_and_record_fed_training(ctx):
         L.call("pb_host_free", p)
 
 
-@pytest.mark.parametrize("layer", [4, 7])
+@pytest.mark.parametrize("layer", [1, 4, 7])
 @pytest.mark.parametrize("batch", [64, 301])
 def test_conv_weight_gradient_tensor_core_large_batch(ctx, layer, batch):
-    """The mma.sync 3xTF32 weight-gradient kernel (csrc/conv_wgrad_mma.cu) walks several
+    """The mma.sync 3xTF32 weight-gradient kernels (csrc/conv_wgrad_mma.cu: channels as the
+    M tile for layers 4 and 7, filters as the M tile and (channel, fx) as N for the RGB
+    layer 1) walk several
     samples per CTA with per-warp register accumulators and per-(CTA, row band) partials;
     all three update modes against the oracle's gradient sum over the whole batch."""
     name = "cifar"

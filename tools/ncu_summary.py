@@ -84,6 +84,7 @@ def main():
             (r"conv_wgrad_ws_kernel<5, 5, 4, 32", "convolution_layer_1:weight_update"),
             (r"conv_wgrad_ws_kernel<5, 5, 4, 16", "convolution_layer_4:weight_update"),
             (r"conv_wgrad_ws_kernel<5, 5, 4, 8", "convolution_layer_7:weight_update"),
+            (r"conv_wgrad_mma_rgb_kernel<unnamed>::NCfg<3, 16, 32>", "convolution_layer_1:weight_update"),
             (r"conv_wgrad_mma_kernel<unnamed>::WCfg<16, 20, 16>", "convolution_layer_4:weight_update"),
             (r"conv_wgrad_mma_kernel<unnamed>::WCfg<20, 20, 8>", "convolution_layer_7:weight_update"),
             (r"UCfg<3, 16, 32, 32, 5, 0, 0>, 2>", "convolution_layer_1:evaluate+activation+pool (tcgen05)"),
