@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "umma.cuh"
 
 namespace pb {
 namespace {
@@ -36,6 +37,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       "{%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// arrives on `bar` once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar))
+               : "memory");
 }
 
 __device__ __forceinline__ void split(float x, uint32_t &hi, uint32_t &lo) {
@@ -321,32 +328,50 @@ struct NCfg {
 };
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, 1)
+__global__ void __launch_bounds__(C::THREADS + 32, 1)
 conv_wgrad_mma_rgb_kernel(const float *__restrict__ In, const float *__restrict__ G,
                           float *__restrict__ partial, int batch, int samples_per_cta) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, slice = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < C::MAIN_ELEMS; i += C::THREADS) smem[i] = 0.0f;
+  __shared__ uint64_t full_bar[2], empty_bar[2];
+  for (int i = tid; i < C::MAIN_ELEMS; i += C::THREADS + 32) smem[i] = 0.0f;
+  if (tid == 0) {
+    for (int st = 0; st < 2; ++st) {
+      umma::mbar_init(&full_bar[st], 32);
+      umma::mbar_init(&empty_bar[st], C::WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   const int b0 = blockIdx.x * samples_per_cta;
   const int b1 = min(batch, b0 + samples_per_cta);
 
-  auto load = [&](int st, int b) {
+  auto load = [&](int st, int b) {  // producer warp only
     float *in_s = smem + st * C::STAGE, *g_s = in_s + C::IN_ELEMS;
     const float *src = In + (int64_t)b * C::IC * C::S * C::S;
-    for (int e = tid; e < C::IC * C::S * C::S / 4; e += C::THREADS) {
+    for (int e = lane; e < C::IC * C::S * C::S / 4; e += 32) {
       const int x4 = e % (C::S / 4), r = e / (C::S / 4);
       const int y = r % C::S, ic = r / C::S;
       __pipeline_memcpy_async(in_s + ic * C::PLANE + (y + C::PADW) * C::PITCH + C::LEFT + 4 * x4,
                               src + 4 * e, 16);
     }
     const float *gs = G + (int64_t)b * C::OC * C::S * C::S;
-    for (int e = tid; e < C::OC * C::S * C::S / 4; e += C::THREADS) {
+    for (int e = lane; e < C::OC * C::S * C::S / 4; e += 32) {
       const int q = e % (C::S * C::S / 4), oc = e / (C::S * C::S / 4);
       __pipeline_memcpy_async(g_s + oc * C::GPLANE + 4 * q, gs + 4 * e, 16);
     }
   };
+  if (slice == C::WARPS) {
+    for (int b = b0; b < b1; ++b) {
+      const int i = b - b0, st = i & 1;
+      umma::mbar_wait(&empty_bar[st], ((i >> 1) & 1) ^ 1);
+      load(st, b);
+      cp_async_arrive(&full_bar[st]);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+  }
 
   // this lane's column n = 8nt + g of the B fragments = (channel, fx); columns past
   // IC*F read channel IC-1 (their products land in D columns that are never stored)
@@ -366,14 +391,9 @@ conv_wgrad_mma_rgb_kernel(const float *__restrict__ In, const float *__restrict_
       for (int i = 0; i < 4; ++i) acc[fy][nt][i] = 0.0f;
   float bias_lo = 0.0f, bias_hi = 0.0f;  // filters g and g + 8
 
-  if (b0 < b1) load(0, b0);
-  __pipeline_commit();
-  for (int b = b0; b < b1; ++b) {
+  for (int b = b0; b < b1 && slice < C::WARPS; ++b) {
     const int st = (b - b0) & 1;
-    if (b + 1 < b1) load(st ^ 1, b + 1);
-    __pipeline_commit();
-    __pipeline_wait_prior(1);
-    __syncthreads();
+    umma::mbar_wait(&full_bar[st], ((b - b0) >> 1) & 1);
     const float *in_s = smem + st * C::STAGE, *g_s = in_s + C::IN_ELEMS;
 #pragma unroll 1
     for (int yy = 0; yy < C::RPS; ++yy) {
@@ -415,9 +435,10 @@ conv_wgrad_mma_rgb_kernel(const float *__restrict__ In, const float *__restrict_
           for (int nt = 0; nt < C::NT; ++nt) mma_tf32(acc[fy][nt], ah, bh[fy][nt]);
       }
     }
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(&empty_bar[st]);
   }
-  __pipeline_wait_prior(0);
+  __syncthreads();
 
   // lanes t = 0..3 hold disjoint pixel subsets of filters g / g + 8
   bias_lo += __shfl_xor_sync(0xffffffffu, bias_lo, 1);
@@ -509,7 +530,7 @@ int launch_rgb(pb_context *ctx, const float *I, const float *Wt, const float *G,
   const int spc = (batch + n_cta - 1) / n_cta;
   const int grid = (batch + spc - 1) / spc;
   if (ensure_workspace(ctx, (size_t)grid * C::ROW)) return 1;
-  kern<<<grid, C::THREADS, C::SMEM, ctx->stream>>>(I, G, ctx->workspace, batch, spc);
+  kern<<<grid, C::THREADS + 32, C::SMEM, ctx->stream>>>(I, G, ctx->workspace, batch, spc);
   PB_LAUNCHED(ctx);
   wgrad_mma_rgb_reduce_kernel<C><<<pb_div_up(C::ROW, 32), 256, 0, ctx->stream>>>(
       ctx->workspace, grid, Wt, out, lr, mode);
