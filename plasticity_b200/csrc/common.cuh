@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "plasticity_b200.h"
 
@@ -22,6 +23,9 @@ struct pb_context {
   // Re-tiled convolution weights of the implicit-GEMM kernel (conv_gemm_umma.cu).
   float *aux = nullptr;
   size_t aux_elems = 0;
+  // Side streams whose work pb_context_finish must also wait for (result read-back of
+  // the host-fed training pipeline).
+  std::vector<cudaStream_t> side_streams;
 };
 
 struct pb_nnet;

@@ -125,6 +125,7 @@ int pb_context_destroy(pb_context *ctx) {
 int pb_context_finish(pb_context *ctx) {
   PB_CHECK(ctx, "pb_context_finish: null ctx");
   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (cudaStream_t st : ctx->side_streams) PB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -56,6 +56,11 @@ struct pb_nnet {
     cudaStream_t copy = nullptr;
     float *x[2] = {nullptr, nullptr}, *e[2] = {nullptr, nullptr};
     uint8_t *rec[2] = {nullptr, nullptr};  // raw byte records (pb_nnet_batch_train_host_records)
+    // result read-back off the compute stream: the step's outputs are copied to y[s] by a
+    // kernel, the D2H DMA of y[s] runs on `out` while the next step computes
+    cudaStream_t out = nullptr;
+    float *y[2] = {nullptr, nullptr};
+    cudaEvent_t y_ready[2] = {nullptr, nullptr};
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
     int64_t cap = 0;
     uint64_t calls = 0;
@@ -385,9 +390,18 @@ int pb_nnet_destroy(pb_nnet *net) {
     cudaStreamSynchronize(net->pipe.copy);
     for (int i = 0; i < 2; ++i) {
       cudaFree(net->pipe.x[i]); cudaFree(net->pipe.e[i]); cudaFree(net->pipe.rec[i]);
+      cudaFree(net->pipe.y[i]);
+      if (net->pipe.y_ready[i]) cudaEventDestroy(net->pipe.y_ready[i]);
       cudaEventDestroy(net->pipe.copied[i]); cudaEventDestroy(net->pipe.consumed[i]);
     }
     cudaStreamDestroy(net->pipe.copy);
+    if (net->pipe.out) {
+      cudaStreamSynchronize(net->pipe.out);
+      auto &ss = net->ctx->side_streams;
+      for (size_t i = 0; i < ss.size(); ++i)
+        if (ss[i] == net->pipe.out) { ss.erase(ss.begin() + i); break; }
+      cudaStreamDestroy(net->pipe.out);
+    }
   }
   if (net->train_exec) cudaGraphExecDestroy(net->train_exec);
   cudaFree(net->weights); cudaFree(net->deltas);
@@ -738,9 +752,26 @@ static int batch_train_host_impl(pb_nnet *net, pb_comm *comm, const float *h_ins
            : pb_nnet_batch_train(net, p.x[s], p.e[s], batch))
     return 1;
   PB_CUDA(cudaEventRecord(p.consumed[s], ctx->stream));
-  if (h_outputs)
-    PB_CUDA(cudaMemcpyAsync(h_outputs, net->outputs.back(), sizeof(float) * (size_t)(batch * nout),
-                            cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_outputs) {
+    if (!p.out) {
+      PB_CUDA(cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking));
+      ctx->side_streams.push_back(p.out);
+      for (int i = 0; i < 2; ++i) {
+        PB_CUDA(cudaMalloc((void **)&p.y[i], sizeof(float) * (size_t)(p.cap * nout)));
+        PB_CUDA(cudaEventCreateWithFlags(&p.y_ready[i], cudaEventDisableTiming));
+      }
+    }
+    // y[s] was last read by the D2H of two calls ago, which the `out` stream has queued
+    // long before: stream order on `out` plus this event keep reader and writer apart
+    if (p.calls >= 2) PB_CUDA(cudaStreamWaitEvent(ctx->stream, p.y_ready[s], 0));
+    if (pb_buffer_copy(ctx, p.y[s], net->outputs.back(), (size_t)(batch * nout))) return 1;
+    cudaEvent_t snap = p.copied[s];  // reuse: `copied[s]` has been waited on already
+    PB_CUDA(cudaEventRecord(snap, ctx->stream));
+    PB_CUDA(cudaStreamWaitEvent(p.out, snap, 0));
+    PB_CUDA(cudaMemcpyAsync(h_outputs, p.y[s], sizeof(float) * (size_t)(batch * nout),
+                            cudaMemcpyDeviceToHost, p.out));
+    PB_CUDA(cudaEventRecord(p.y_ready[s], p.out));
+  }
   p.calls++;
   return 0;
 }
