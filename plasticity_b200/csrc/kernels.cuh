@@ -94,6 +94,14 @@ int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *conv, int 
 int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *I,
                             const float *W, float *O, float *O2, int act, int64_t batch);
 
+// train_small.cu: n per-sample SGD steps of a small all-dense network as ONE persistent
+// single-CTA kernel (weights, activations and gradients in shared memory); -1 outside the
+// envelope (the graph-replayed layer-by-layer loop then runs).
+int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
+                     const int64_t *w_off, int64_t total_w, int loss, float *weights,
+                     const float *lr, const float *d_ins, const float *d_expected,
+                     int64_t n_samples);
+
 // records.cu: pb_records_decode on an explicit stream.
 int records_decode_on(pb_context *ctx, cudaStream_t stream, const uint8_t *d_records,
                       float *d_inputs, float *d_expected, int64_t n_records, int64_t sample_size,

@@ -536,6 +536,13 @@ int pb_nnet_train_loop(pb_nnet *net, const float *d_ins, const float *d_expected
   PB_CHECK(net && d_ins && d_expected, "pb_nnet_train_loop: null");
   if (n_samples <= 0) return 0;
   pb_context *ctx = net->ctx;
+  {
+    // small all-dense networks (the circle MLP): the whole loop is one persistent kernel
+    const int rc = pb::train_loop_small(ctx, net->layers.data(), (int)net->layers.size(),
+                                        net->w_off.data(), net->total_w, net->loss, net->weights,
+                                        net->lr, d_ins, d_expected, n_samples);
+    if (rc >= 0) return rc;
+  }
   if (!net->train_exec) {
     // Capture ONE Train() (fetch sample -> forward -> error gradient ->
     // reverse loop with in-place SGD -> advance cursor) into a CUDA graph.
