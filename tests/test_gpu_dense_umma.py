@@ -110,3 +110,28 @@ def test_wide_mlp_batch_train_step(ctx):
     got = util.read_product_weights(net, S)
     util.assert_close(got - w0, w_ref - w0, "wide MLP BatchTrain deltas", rtol=2e-4, atol_scale=2e-5)
     util.assert_close(got, w_ref, "wide MLP BatchTrain weights")
+
+
+def test_wide_classifier_head(ctx):
+    """dense 4096 -> 10 + identity + softmax + cross-entropy (the head of BASELINE.json
+    config 4: too wide for the fused head kernel's shared-memory budget, so the tensor-core
+    dense kernels with split-K, the softmax / error kernels and the skinny weight gradient
+    run layer by layer): one gradient-sum step against the oracle."""
+    n_in, B = 4096, 72
+    spec = f"loss ce\nact {n_in} identity\ndense {n_in} 10\nact 10 identity\nsoftmax 10\n"
+    S = po.RestatedNet(spec)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(11)
+    w0 = util.xavier_like(S, rng)
+    xs = util.f32(rng.normal(0, 1, (B, n_in)))
+    es = np.zeros((B, 10))
+    es[np.arange(B), rng.integers(0, 10, B)] = 1.0
+    lr = 1e-3
+    net = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=B)
+    net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+    util.load_product_weights(net, S, w0)
+    w_ref = w0.copy()
+    S.batch_train(xs.copy(), es.copy(), w_ref, lr)
+    net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), B)
+    got = util.read_product_weights(net, S)
+    util.assert_close(got - w0, w_ref - w0, "wide head deltas", rtol=2e-4, atol_scale=2e-5)
