@@ -755,26 +755,30 @@ static int batch_train_host_impl(pb_nnet *net, pb_comm *comm, const float *h_ins
   }
   PB_CUDA(cudaEventRecord(p.copied[s], p.copy));
   PB_CUDA(cudaStreamWaitEvent(ctx->stream, p.copied[s], 0));
-  if (comm ? pb_nnet_batch_train_dp(net, comm, p.x[s], p.e[s], batch)
-           : pb_nnet_batch_train(net, p.x[s], p.e[s], batch))
-    return 1;
+  if (h_outputs && !p.out) {
+    PB_CUDA(cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking));
+    ctx->side_streams.push_back(p.out);
+    for (int i = 0; i < 2; ++i) {
+      PB_CUDA(cudaMalloc((void **)&p.y[i], sizeof(float) * (size_t)(p.cap * nout)));
+      PB_CUDA(cudaEventCreateWithFlags(&p.y_ready[i], cudaEventDisableTiming));
+    }
+  }
+  // The step writes the network's outputs straight into y[s] (the last layer's output
+  // buffer is redirected for this call): the D2H DMA then runs on the side stream while
+  // the next step computes into the other buffer.  y[s] was last read by the D2H of two
+  // calls ago.
+  float *saved_out = net->outputs.back();
+  if (h_outputs) {
+    if (p.calls >= 2) PB_CUDA(cudaStreamWaitEvent(ctx->stream, p.y_ready[s], 0));
+    net->outputs.back() = p.y[s];
+  }
+  const int rc = comm ? pb_nnet_batch_train_dp(net, comm, p.x[s], p.e[s], batch)
+                      : pb_nnet_batch_train(net, p.x[s], p.e[s], batch);
+  net->outputs.back() = saved_out;
+  if (rc) return 1;
   PB_CUDA(cudaEventRecord(p.consumed[s], ctx->stream));
   if (h_outputs) {
-    if (!p.out) {
-      PB_CUDA(cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking));
-      ctx->side_streams.push_back(p.out);
-      for (int i = 0; i < 2; ++i) {
-        PB_CUDA(cudaMalloc((void **)&p.y[i], sizeof(float) * (size_t)(p.cap * nout)));
-        PB_CUDA(cudaEventCreateWithFlags(&p.y_ready[i], cudaEventDisableTiming));
-      }
-    }
-    // y[s] was last read by the D2H of two calls ago, which the `out` stream has queued
-    // long before: stream order on `out` plus this event keep reader and writer apart
-    if (p.calls >= 2) PB_CUDA(cudaStreamWaitEvent(ctx->stream, p.y_ready[s], 0));
-    if (pb_buffer_copy(ctx, p.y[s], net->outputs.back(), (size_t)(batch * nout))) return 1;
-    cudaEvent_t snap = p.copied[s];  // reuse: `copied[s]` has been waited on already
-    PB_CUDA(cudaEventRecord(snap, ctx->stream));
-    PB_CUDA(cudaStreamWaitEvent(p.out, snap, 0));
+    PB_CUDA(cudaStreamWaitEvent(p.out, p.consumed[s], 0));
     PB_CUDA(cudaMemcpyAsync(h_outputs, p.y[s], sizeof(float) * (size_t)(batch * nout),
                             cudaMemcpyDeviceToHost, p.out));
     PB_CUDA(cudaEventRecord(p.y_ready[s], p.out));
