@@ -297,6 +297,11 @@ def run_ours(args):
         return float(t.item())
 
     # ---------------- device-resident timing ------------------------------
+    # Set-up, not warm-up: the library records the step for a given (inputs, targets)
+    # pair into a CUDA graph on its second use; touch every resident batch twice so the
+    # W warm-up steps and the K timed steps below are all steady-state replays.
+    for i in range(2 * NB):
+        step_resident(i)
     for i in range(args.warmup):
         step_resident(i)
     barrier()
@@ -338,7 +343,7 @@ def run_ours(args):
                                   C.c_void_p(ho.value + (i % 2) * B * 10 * 4), comm=comm)
 
     def time_e2e(step_fn):
-        for i in range(min(args.warmup, 3)):
+        for i in range(max(min(args.warmup, 3), 4)):  # both staging slots twice (graph capture)
             step_fn(i)
         barrier()
         e2 = torch.cuda.Event(enable_timing=True)

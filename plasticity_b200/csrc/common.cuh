@@ -26,6 +26,8 @@ struct pb_context {
   // Side streams whose work pb_context_finish must also wait for (result read-back of
   // the host-fed training pipeline).
   std::vector<cudaStream_t> side_streams;
+  // bumped whenever workspace / aux are reallocated: captured graphs hold their addresses
+  uint64_t alloc_generation = 0;
 };
 
 struct pb_nnet;

@@ -37,6 +37,7 @@ int ensure_workspace(pb_context *ctx, size_t elems) {
   size_t want = std::max<size_t>(elems, 1 << 20);
   PB_CUDA(cudaMalloc(&ctx->workspace, want * sizeof(float)));
   ctx->workspace_elems = want;
+  ctx->alloc_generation++;
   return 0;
 }
 
@@ -49,6 +50,7 @@ int ensure_aux(pb_context *ctx, size_t elems) {
   size_t want = std::max<size_t>(elems, 1 << 20);
   PB_CUDA(cudaMalloc(&ctx->aux, want * sizeof(float)));
   ctx->aux_elems = want;
+  ctx->alloc_generation++;
   return 0;
 }
 

@@ -104,7 +104,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3) + 2 * NB):  # every batch twice: CUDA-graph capture
         step(i)
     barrier()
     sampler = bench.ClockSampler(local) if rank == 0 else None
