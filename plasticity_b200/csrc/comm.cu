@@ -55,7 +55,8 @@ struct pb_comm {
   float *big_W[kMaxP2pRanks] = {nullptr}, *big_D[kMaxP2pRanks] = {nullptr};
   uint32_t *big_flags[kMaxP2pRanks] = {nullptr};
   uint32_t *big_local_flags = nullptr;
-  uint32_t big_epoch = 0;
+  uint32_t *d_epoch = nullptr;  // step counter of the bucket exchange, bumped ON THE DEVICE
+                                // (one tiny kernel per step) so the step can be a CUDA graph
 };
 
 namespace pb {
@@ -282,7 +283,8 @@ __device__ __forceinline__ void bucket_reduce_apply(const BigPeers &P, int64_t o
 // (544 threads x 96 registers, 194 KiB of shared memory) of the backward pass.
 __global__ void __launch_bounds__(128, 5)
 p2p_bucket_kernel(BigPeers P, int64_t off, int64_t n, int bucket, int rank, int R,
-                  uint32_t epoch, int *timeout_flag) {
+                  const uint32_t *epoch_p, int *timeout_flag) {
+  const uint32_t epoch = *epoch_p;
   uint32_t *mine = P.flags[rank] + (size_t)bucket * 2 * kMaxP2pRanks;
   uint32_t *counter = P.flags[rank] + (size_t)kMaxBuckets * 2 * kMaxP2pRanks + bucket;
   if (threadIdx.x < R) {
@@ -323,6 +325,8 @@ p2p_bucket_kernel(BigPeers P, int64_t off, int64_t n, int bucket, int rank, int 
   }
 }
 
+__global__ void bump_epoch_kernel(uint32_t *epoch) { *epoch += 1; }
+
 // Collective: maps every rank's weight / delta buffers and flag block into this process.
 static int big_setup(pb_comm *c, float *weights, float *deltas, int n_layers) {
   NcclApi *api = nccl_api();
@@ -337,6 +341,8 @@ static int big_setup(pb_comm *c, float *weights, float *deltas, int n_layers) {
   memset(&rec, 0, sizeof(rec));
   if (ok && cudaMalloc((void **)&c->big_local_flags, kBigFlagWords * 4) != cudaSuccess) ok = 0;
   if (ok && cudaMemsetAsync(c->big_local_flags, 0, kBigFlagWords * 4, st) != cudaSuccess) ok = 0;
+  if (ok && cudaMalloc((void **)&c->d_epoch, 4) != cudaSuccess) ok = 0;
+  if (ok && cudaMemsetAsync(c->d_epoch, 0, 4, st) != cudaSuccess) ok = 0;
   if (ok && cudaIpcGetMemHandle(&rec.w, weights) != cudaSuccess) ok = 0;
   if (ok && cudaIpcGetMemHandle(&rec.d, deltas) != cudaSuccess) ok = 0;
   if (ok && cudaIpcGetMemHandle(&rec.f, c->big_local_flags) != cudaSuccess) ok = 0;
@@ -411,7 +417,7 @@ static int p2p_bucket_hook(void *user, int layer, float *d_delta, float *d_weigh
   const int64_t per4 = ((n4 >> 2) + c->n_ranks - 1) / c->n_ranks;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(c->ctx->num_sms, (per4 + 511) / 512));
   p2p_bucket_kernel<<<grid, 128, 0, c->comm_stream>>>(P, off, n4, layer, c->rank, c->n_ranks,
-                                                      c->big_epoch, c->d_timeout);
+                                                      c->d_epoch, c->d_timeout);
   PB_LAUNCHED(c->ctx);
   return 0;
 }
@@ -501,6 +507,7 @@ int pb_comm_destroy(pb_comm *comm) {
       }
     }
     if (comm->big_local_flags) cudaFree(comm->big_local_flags);
+    if (comm->d_epoch) cudaFree(comm->d_epoch);
     if (comm->local) cudaFree(comm->local);
     if (comm->d_timeout) cudaFree(comm->d_timeout);
     api->CommDestroy(comm->comm);
@@ -556,16 +563,30 @@ int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
     // otherwise NCCL all-reduce + accumulate per layer (large buffers) or the paths below
     const bool p2p = comm->big_state == 1;
     if (p2p || n > kMaxP2pFloats) {
-      comm->events_used = 0;
-      if (p2p) comm->big_epoch++;
-      pb::nnet_set_delta_hook(net, p2p ? pb::p2p_bucket_hook : pb::overlap_hook, comm);
-      const int rc = pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch);
-      pb::nnet_set_delta_hook(net, nullptr, nullptr);
-      if (rc) return 1;
-      cudaEvent_t done = pb::next_event(comm);
-      PB_CUDA(cudaEventRecord(done, comm->comm_stream));
-      PB_CUDA(cudaStreamWaitEvent(comm->ctx->stream, done, 0));
-      return 0;
+      struct Body {
+        pb_nnet *net; pb_comm *comm; const float *ins, *exp; int64_t batch; bool p2p;
+      } body{net, comm, d_ins, d_expected, local_batch, p2p};
+      auto run = [](void *u) -> int {
+        Body *b = (Body *)u;
+        pb_comm *c = b->comm;
+        c->events_used = 0;
+        if (b->p2p) {
+          pb::bump_epoch_kernel<<<1, 1, 0, c->ctx->stream>>>(c->d_epoch);
+          PB_LAUNCHED(c->ctx);
+        }
+        pb::nnet_set_delta_hook(b->net, b->p2p ? pb::p2p_bucket_hook : pb::overlap_hook, c);
+        const int rc = pb_nnet_batch_gradients(b->net, b->ins, b->exp, b->batch);
+        pb::nnet_set_delta_hook(b->net, nullptr, nullptr);
+        if (rc) return 1;
+        cudaEvent_t done = pb::next_event(c);
+        PB_CUDA(cudaEventRecord(done, c->comm_stream));
+        PB_CUDA(cudaStreamWaitEvent(c->ctx->stream, done, 0));
+        return 0;
+      };
+      // the peer-memory step is device-driven end to end (flags, step counter): it is
+      // recorded into a CUDA graph like the single-GPU step; the NCCL variant stays eager
+      if (p2p) return pb::nnet_run_graphed(net, d_ins, d_expected, local_batch, 1, run, &body);
+      return run(&body);
     }
   }
   if (pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch)) return 1;

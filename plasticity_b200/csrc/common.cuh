@@ -40,6 +40,10 @@ namespace pb {
 typedef int (*delta_hook_fn)(void *user, int layer, float *d_delta, float *d_weights, int64_t n);
 void nnet_set_delta_hook(pb_nnet *net, delta_hook_fn hook, void *user);
 
+// nnet.cu: run a training-step body eagerly / captured / replayed as a CUDA graph.
+int nnet_run_graphed(pb_nnet *net, const float *d_ins, const float *d_expected, int64_t batch,
+                     int tag, int (*body)(void *), void *user);
+
 void set_error(const std::string &msg);
 int fail(const std::string &msg);
 int ensure_stage(pb_context *ctx, size_t elems);

@@ -75,6 +75,7 @@ struct pb_nnet {
   struct StepGraph {
     const float *ins = nullptr, *expected = nullptr, *out = nullptr;  // out: last layer's buffer
     int64_t batch = 0;
+    int tag = 0;              // which step body (0: in-place step, 1: data-parallel step)
     uint64_t generation = 0;  // ctx->alloc_generation at capture (workspace addresses)
     int uses = 0;
     cudaGraphExec_t exec = nullptr;
@@ -297,6 +298,75 @@ static int train_step(pb_nnet *net, const float *d_in, const float *d_expected,
   float *g = nullptr;
   if (backward(net, d_in, 1, net->grad_a, net->grad_b, PB_NEW_WEIGHTS, true, &g)) return 1;
   if (d_input_gradients) return pb_buffer_copy(ctx, d_input_gradients, g, net->ni[0]);
+  return 0;
+}
+
+
+// Runs one training-step body, recorded into a CUDA graph the second time it is called
+// with the same (inputs, targets, output buffer, batch, tag) and replayed afterwards.
+// First use: eager (one-off buffers never pay for a capture; the eager run also sizes the
+// workspaces).  Second use: eager once more, then the same call sequence is captured —
+// capturing executes nothing.  Graphs are dropped when a workspace they captured moved.
+int nnet_run_graphed(pb_nnet *net, const float *d_ins, const float *d_expected, int64_t batch,
+                     int tag, int (*body)(void *), void *user) {
+  if (!net->use_graphs || net->profiling) return body(user);
+  pb_context *ctx = net->ctx;
+  pb_nnet::StepGraph *sg = nullptr;
+  const float *out_now = net->outputs.back();
+  for (auto &g : net->step_graphs)
+    if (g.ins == d_ins && g.expected == d_expected && g.out == out_now && g.batch == batch &&
+        g.tag == tag)
+      sg = &g;
+  if (!sg) {
+    pb_nnet::StepGraph fresh;
+    fresh.ins = d_ins; fresh.expected = d_expected; fresh.out = out_now; fresh.batch = batch;
+    fresh.tag = tag;
+    if (net->step_graphs.size() < 32) {
+      net->step_graphs.push_back(fresh);
+      sg = &net->step_graphs.back();
+    } else {  // ring replacement
+      sg = &net->step_graphs[net->step_graph_next++ % 32];
+      if (sg->exec) cudaGraphExecDestroy(sg->exec);
+      *sg = fresh;
+    }
+  }
+  if (sg->exec && sg->generation != ctx->alloc_generation) {
+    cudaGraphExecDestroy(sg->exec);  // the workspace moved since the capture
+    sg->exec = nullptr;
+    sg->uses = 0;
+  }
+  if (sg->exec) {
+    PB_CUDA(cudaGraphLaunch(sg->exec, ctx->stream));
+    ctx->launches += sg->launches;
+    return 0;
+  }
+  if (body(user)) return 1;
+  if (sg->uses++ == 0) return 0;
+  cudaGraph_t graph = nullptr;
+  const uint64_t before = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    net->use_graphs = false;
+    return 0;
+  }
+  const int rc = body(user);
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  sg->launches = ctx->launches - before;
+  ctx->launches = before;
+  if (rc || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    net->use_graphs = false;  // something in the step is not capturable: stay eager
+    return 0;
+  }
+  sg->generation = ctx->alloc_generation;
+  const cudaError_t ei = cudaGraphInstantiate(&sg->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) {
+    sg->exec = nullptr;
+    cudaGetLastError();
+    net->use_graphs = false;
+  }
   return 0;
 }
 
@@ -730,66 +800,14 @@ int pb_nnet_batch_train(pb_nnet *net, const float *d_ins, const float *d_expecte
   // One chunk: the SGD update is fused into the weight-gradient kernels.  Several chunks
   // must all see the batch-start weights, so they go through the delta buffer.
   if (batch <= net->max_batch && net->fuse) {
-    if (!net->use_graphs || net->profiling) return batch_pass(net, d_ins, d_expected, batch, true);
-    pb_context *ctx = net->ctx;
-    pb_nnet::StepGraph *sg = nullptr;
-    const float *out_now = net->outputs.back();
-    for (auto &g : net->step_graphs)
-      if (g.ins == d_ins && g.expected == d_expected && g.out == out_now && g.batch == batch)
-        sg = &g;
-    if (!sg) {
-      pb_nnet::StepGraph fresh;
-      fresh.ins = d_ins; fresh.expected = d_expected; fresh.out = out_now; fresh.batch = batch;
-      if (net->step_graphs.size() < 32) {
-        net->step_graphs.push_back(fresh);
-        sg = &net->step_graphs.back();
-      } else {  // ring replacement
-        sg = &net->step_graphs[net->step_graph_next++ % 32];
-        if (sg->exec) cudaGraphExecDestroy(sg->exec);
-        *sg = fresh;
-      }
-    }
-    if (sg->exec && sg->generation != ctx->alloc_generation) {
-      cudaGraphExecDestroy(sg->exec);  // the workspace moved since the capture
-      sg->exec = nullptr;
-      sg->uses = 0;
-    }
-    if (sg->exec) {
-      PB_CUDA(cudaGraphLaunch(sg->exec, ctx->stream));
-      ctx->launches += sg->launches;
-      return 0;
-    }
-    // First use of this (inputs, targets, outputs, batch): eager (one-off buffers never pay
-    // for a capture).  Second use: run the step eagerly once more, then record the same call
-    // sequence into a graph — capturing executes nothing — for every later use.
-    if (batch_pass(net, d_ins, d_expected, batch, true)) return 1;
-    if (sg->uses++ == 0) return 0;
-    cudaGraph_t graph = nullptr;
-    const uint64_t before = ctx->launches;
-    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-      cudaGetLastError();
-      net->use_graphs = false;
-      return 0;
-    }
-    const int rc = batch_pass(net, d_ins, d_expected, batch, true);
-    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-    sg->launches = ctx->launches - before;
-    ctx->launches = before;
-    if (rc || e != cudaSuccess || !graph) {
-      if (graph) cudaGraphDestroy(graph);
-      cudaGetLastError();
-      net->use_graphs = false;  // something in the plan is not capturable: stay eager
-      return 0;
-    }
-    sg->generation = ctx->alloc_generation;
-    const cudaError_t ei = cudaGraphInstantiate(&sg->exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ei != cudaSuccess) {
-      sg->exec = nullptr;
-      cudaGetLastError();
-      net->use_graphs = false;
-    }
-    return 0;
+    struct Body { pb_nnet *net; const float *ins, *exp; int64_t batch; } body{net, d_ins, d_expected, batch};
+    return pb::nnet_run_graphed(
+        net, d_ins, d_expected, batch, 0,
+        [](void *u) {
+          Body *b = (Body *)u;
+          return batch_pass(b->net, b->ins, b->exp, b->batch, true);
+        },
+        &body);
   }
   if (batch_pass(net, d_ins, d_expected, batch, false)) return 1;
   return pb_nnet_apply_deltas(net);
