@@ -324,9 +324,15 @@ int nnet_run_graphed(pb_nnet *net, const float *d_ins, const float *d_expected, 
     if (net->step_graphs.size() < 32) {
       net->step_graphs.push_back(fresh);
       sg = &net->step_graphs.back();
-    } else {  // ring replacement
-      sg = &net->step_graphs[net->step_graph_next++ % 32];
-      if (sg->exec) cudaGraphExecDestroy(sg->exec);
+    } else {
+      // replace, in ring order, an entry that never got a graph (a data set with more
+      // batches than slots cycles through here and simply stays eager); recorded graphs
+      // are never evicted by one-off keys
+      for (int tries = 0; tries < 32 && !sg; ++tries) {
+        pb_nnet::StepGraph *cand = &net->step_graphs[net->step_graph_next++ % 32];
+        if (!cand->exec) sg = cand;
+      }
+      if (!sg) return body(user);
       *sg = fresh;
     }
   }
