@@ -138,6 +138,12 @@ def main():
         except Exception:
             pass
         tf32x3_peak = peaks.get("bf16_tflops", 1590.0) / 2 / 3
+        recorded = {}
+        try:  # tools/cpu_baselines.py on the GPU box: TF32 matmul peak + CPU rates of this config
+            recorded = json.load(open(os.path.join(ROOT, "profiles", "r01_cpu_baselines.json")))
+        except Exception:
+            pass
+        tf32x3_measured = recorded.get("tf32_tflops_burst", 0.0) / 3 or None
         top = rows[0]
         line = {
             "metric": "wide_mlp_train_samples_per_sec", "value": world * B * args.steps / (ms * 1e-3),
@@ -157,6 +163,14 @@ def main():
                          "vs_fp32_ffma_peak": top["tflops"] / tf.value},
             "step_kernels": rows,
         }
+        line["roofline"]["peak_tf32_matmul_measured_div3"] = tf32x3_measured
+        if tf32x3_measured:
+            line["roofline"]["frac_of_measured_tf32"] = top["tflops"] / tf32x3_measured
+        if "wide_mlp_train" in recorded:
+            cb = dict(recorded["wide_mlp_train"])
+            cb["cores"] = recorded.get("host_cores")
+            cb["note"] = "recorded by tools/cpu_baselines.py on the GPU box's host (not timed in this run)"
+            line["cpu_baseline"] = cb
         print(json.dumps(line))
     barrier()
     if comm is not None:
