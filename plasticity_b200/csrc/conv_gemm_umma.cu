@@ -146,7 +146,9 @@ struct ConvPolicy {
     __device__ __forceinline__ void store(float4 *hi, int p) const { store_row16<LA>(v, hi, p); }
   };
 
-  struct B : MatrixOperand<OP_KV, BN, LB> {
+  static constexpr int kMinBN = 64;
+  template <int BN_T>
+  struct B : MatrixOperand<OP_KV, BN_T, BN_T + 2> {
     __device__ __forceinline__ void init(const Args &g) {
       this->setup(g.Wk, g.Kp, g.N, g.Kp, g.mma_n);
     }

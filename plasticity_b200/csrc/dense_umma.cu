@@ -46,7 +46,10 @@ struct DensePolicy {
     __device__ __forceinline__ void tile(const Args &, int t, int) { this->set_tile(t); }
     __device__ __forceinline__ void load(const Args &, int ks, int p) { this->load_stage(ks, p); }
   };
-  struct B : MatrixOperand<BMODE, BN, LB> {
+  // the transposing (MN) loader maps one row per thread of the 128-thread group
+  static constexpr int kMinBN = BMODE == OP_MN ? 128 : 64;
+  template <int BN_T>
+  struct B : MatrixOperand<BMODE, BN_T, BN_T + 2> {
     __device__ __forceinline__ void init(const Args &g) { this->setup(g.B, g.ldb, g.N, g.K, g.mma_n); }
     __device__ __forceinline__ void tile(const Args &, int t, int) { this->set_tile(t); }
     __device__ __forceinline__ void load(const Args &, int ks, int p) { this->load_stage(ks, p); }

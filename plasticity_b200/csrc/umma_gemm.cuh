@@ -29,7 +29,8 @@
 //   struct Args : GemmCore {...};
 //   struct A { void init(const Args&); void tile(const Args&, int tile_m, int p);
 //              void load(const Args&, int k_stage, int p); void store(float4 *hi, int p) const; };
-//   struct B { same, with tile_n };            (p = thread index in the 128-thread group)
+//   template <int BN_T> struct B { same, with tile_n; BN_T rows per tile };
+//                                              (p = thread index in the 128-thread group)
 //   static constexpr int kEpiCols (16 or 32); static constexpr bool kEpiTranspose;
 //   static void store_cols(const Args&, int row0, int lane, int n0, const float (&v)[kEpiCols],
 //                          int n_valid, float *stage);   (v = columns n0.. of row row0+lane;
@@ -54,18 +55,30 @@ constexpr int kThreads = (kEpiWarps + 1) * 32 + kGroups * kGroupThreads;  // 544
 // Plane pitches in 16-byte units.  = 2 (mod 8): the float4 stores of a quarter
 // warp (2 rows x 4 chunks) and the scalar stores of a warp (2 rows x 16 k) hit
 // distinct banks.
-constexpr int LA = BM + 2, LB = BN + 2;
+constexpr int LA = BM + 2;
 constexpr int CHUNKS = BK / 4;
-constexpr int STAGE_UNITS = 2 * CHUNKS * (LA + LB);  // float4 per stage
-// 194.1 KiB: stays under the 196 KiB shared-memory carve-out step, which leaves 60 KiB
-// of L1 for the operand gathers (the next step, 228 KiB, leaves 28).
-constexpr size_t kSmem = 16 * (size_t)STAGES * STAGE_UNITS + 8 * (2 * STAGES + 4) + 16;
+// The N extent of the CTA tile is a template parameter (256 / 128 / 64): problems with few
+// columns (a convolution with 64 filters) stage fewer B rows per K step and get more
+// shared-memory stages for the same budget, i.e. more load latency hidden per MMA cycle.
+template <int BN_T>
+struct Geo {
+  static constexpr int LB = BN_T + 2;
+  static constexpr int STAGE_UNITS = 2 * CHUNKS * (LA + LB);  // float4 per stage
+  static constexpr int STAGES = BN_T == 256 ? 4 : (BN_T == 128 ? 5 : 7);
+  // + 1 KiB the system reserves per CTA <= 196 KiB: stays under that shared-memory
+  // carve-out step, which leaves 60 KiB of L1 for the operand gathers (the next step,
+  // 228 KiB, leaves 28 and costs 10-40 % on the gather-heavy layers).
+  static constexpr size_t kSmem = 16 * (size_t)STAGES * STAGE_UNITS + 8 * (2 * STAGES + 4) + 16;
+  static constexpr uint32_t TMEM_COLS = 2 * BN_T;  // two accumulator stages
+  static_assert(kSmem + 1024 <= 196 * 1024, "shared-memory budget");
+};
+constexpr int LB = Geo<BN>::LB;  // plane pitch of the full-width tile (policies' default)
 // Optional (policy P::kEpiTranspose): per epilogue warp a 32 x 32 transpose tile, pitch 33
 // (conflict-free both ways), for policies whose C rows must be written by whole warps.
 constexpr int kEpiStage = 32 * 33;
-template <class P>
+template <class P, int BN_T>
 constexpr size_t smem_bytes() {
-  return kSmem + (P::kEpiTranspose ? 4 * (size_t)kEpiWarps * kEpiStage : 0);
+  return Geo<BN_T>::kSmem + (P::kEpiTranspose ? 4 * (size_t)kEpiWarps * kEpiStage : 0);
 }
 
 struct GemmCore {
@@ -221,8 +234,10 @@ struct MatrixOperand {
 #else
 #define PB_GEMM_BOUNDS __launch_bounds__(kThreads, 1)
 #endif
-template <class P>
+template <class P, int BN_T>
 __global__ void PB_GEMM_BOUNDS umma_gemm_kernel(const __grid_constant__ typename P::Args g) {
+  using G_ = Geo<BN_T>;
+  constexpr int STAGES = G_::STAGES, STAGE_UNITS = G_::STAGE_UNITS, LB = G_::LB, BN = BN_T;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float4 *stage_s = reinterpret_cast<float4 *>(smem_raw);  // [STAGES][STAGE_UNITS]
   uint64_t *bars = reinterpret_cast<uint64_t *>(stage_s + STAGES * STAGE_UNITS);
@@ -240,7 +255,7 @@ __global__ void PB_GEMM_BOUNDS umma_gemm_kernel(const __grid_constant__ typename
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_ptr)),
-                 "r"(512u)
+                 "r"(G_::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -267,7 +282,7 @@ __global__ void PB_GEMM_BOUNDS umma_gemm_kernel(const __grid_constant__ typename
     const int pt = tid - (kEpiWarps + 1) * 32;
     const int grp = pt / kGroupThreads, p = pt % kGroupThreads;
     typename P::A opa;
-    typename P::B opb;
+    typename P::template B<BN_T> opb;
     opa.init(g);
     opb.init(g);
     int it = 0;  // K-stage counter across all work items of this CTA
@@ -371,7 +386,8 @@ __global__ void PB_GEMM_BOUNDS umma_gemm_kernel(const __grid_constant__ typename
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(G_::TMEM_COLS)
                  : "memory");
   }
 }
@@ -390,20 +406,20 @@ __global__ void splitk_reduce_kernel(const typename P::Args g) {
 }
 
 // Fills the GemmCore fields (tiling, split-K) and launches.  K = number of k values.
-template <class P>
-int launch_gemm(pb_context *ctx, typename P::Args g, int M, int N, int K) {
-  auto kern = umma_gemm_kernel<P>;
+template <class P, int BN_T>
+int launch_gemm_bn(pb_context *ctx, typename P::Args g, int M, int N, int K) {
+  auto kern = umma_gemm_kernel<P, BN_T>;
   static bool configured = false;
   if (!configured) {
     PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem_bytes<P>()));
+                                 (int)smem_bytes<P, BN_T>()));
     configured = true;
   }
   g.M = M;
   g.N = N;
   g.k_stages = pb_div_up(K, BK);
-  g.mma_n = std::min(BN, pb_div_up(N, 16) * 16);
-  const int tiles = pb_div_up(M, BM) * pb_div_up(N, BN);
+  g.mma_n = std::min(BN_T, pb_div_up(N, 16) * 16);
+  const int tiles = pb_div_up(M, BM) * pb_div_up(N, BN_T);
   // Split K when the tiles alone leave most SMs idle; every split keeps at least
   // 16 K stages so the pipeline fill stays amortised.
   int splits = 1;
@@ -417,13 +433,22 @@ int launch_gemm(pb_context *ctx, typename P::Args g, int M, int N, int K) {
     g.partial = ctx->workspace;
   }
   const int grid = std::min(tiles * g.splits, ctx->num_sms);
-  kern<<<grid, kThreads, smem_bytes<P>(), ctx->stream>>>(g);
+  kern<<<grid, kThreads, smem_bytes<P, BN_T>(), ctx->stream>>>(g);
   PB_LAUNCHED(ctx);
   if (g.splits > 1) {
     splitk_reduce_kernel<P><<<pb_ew_grid(ctx, (int64_t)M * N, 256), 256, 0, ctx->stream>>>(g);
     PB_LAUNCHED(ctx);
   }
   return 0;
+}
+
+// Tile width by problem width.  P::kMinBN: the narrowest tile the policy's B loader
+// supports (its row mapping needs at least that many rows).
+template <class P>
+int launch_gemm(pb_context *ctx, const typename P::Args &g, int M, int N, int K) {
+  if (N <= 64 && P::kMinBN <= 64) return launch_gemm_bn<P, 64>(ctx, g, M, N, K);
+  if (N <= 128 && P::kMinBN <= 128) return launch_gemm_bn<P, 128>(ctx, g, M, N, K);
+  return launch_gemm_bn<P, 256>(ctx, g, M, N, K);
 }
 
 inline bool umma_gemm_enabled() {
