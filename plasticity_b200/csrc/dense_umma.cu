@@ -66,7 +66,7 @@ struct DensePolicy {
   // contiguous 128-byte run of one row (also the read-modify-write of the SGD update).
   static __device__ __forceinline__ void store_cols(const Args &g, int row0, int lane, int n0,
                                                  const float (&v)[32], int nv, float *stage) {
-    if (!TRANSPOSE) {
+    if constexpr (!TRANSPOSE) {
       const int m = row0 + lane;
       if (m >= g.M) return;
       float *crow = g.C + (int64_t)m * g.ldc + n0;
@@ -89,7 +89,7 @@ struct DensePolicy {
       for (int j = 0; j < 32; ++j)
         if (j < nv) store1(g, m, n0 + j, v[j]);
       return;
-    }
+    } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
     __syncwarp();
@@ -123,6 +123,7 @@ struct DensePolicy {
         if (col_ok) *c = stage[r * 33 + lane] + b;
     }
     __syncwarp();
+    }
   }
 };
 

@@ -162,7 +162,7 @@ struct MatrixOperand {
         }
       }
     } else if (MODE == OP_MN) {
-      constexpr int H = ROWS / kGroupThreads;  // row halves per thread (1 or 2)
+      constexpr int H = ROWS >= kGroupThreads ? ROWS / kGroupThreads : 1;  // row halves per thread
       const int r = row0 + p;
       const float *q = base + (int64_t)k0 * ld + r;
       if (interior) {
@@ -213,7 +213,7 @@ struct MatrixOperand {
       }
     } else {
       // KV: value group j = (row (p>>2) + 32j, chunk p&3); MN: group j = (chunk j/H, row p + 128(j%H))
-      constexpr int H = ROWS / kGroupThreads;
+      constexpr int H = ROWS >= kGroupThreads ? ROWS / kGroupThreads : 1;
       hi += MODE == OP_KV ? (p & 3) * L + (p >> 2) : p;
       lo += MODE == OP_KV ? (p & 3) * L + (p >> 2) : p;
 #pragma unroll
