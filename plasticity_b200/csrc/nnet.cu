@@ -307,6 +307,10 @@ static int train_step(pb_nnet *net, const float *d_in, const float *d_expected,
 // First use: eager (one-off buffers never pay for a capture; the eager run also sizes the
 // workspaces).  Second use: eager once more, then the same call sequence is captured —
 // capturing executes nothing.  Graphs are dropped when a workspace they captured moved.
+// distinct (inputs, targets) pairs with a recorded graph per network: a resident data set of
+// up to this many batches replays every step from its second epoch on
+constexpr size_t kMaxStepGraphs = 256;
+
 int nnet_run_graphed(pb_nnet *net, const float *d_ins, const float *d_expected, int64_t batch,
                      int tag, int (*body)(void *), void *user) {
   if (!net->use_graphs || net->profiling) return body(user);
@@ -321,15 +325,15 @@ int nnet_run_graphed(pb_nnet *net, const float *d_ins, const float *d_expected, 
     pb_nnet::StepGraph fresh;
     fresh.ins = d_ins; fresh.expected = d_expected; fresh.out = out_now; fresh.batch = batch;
     fresh.tag = tag;
-    if (net->step_graphs.size() < 32) {
+    if (net->step_graphs.size() < kMaxStepGraphs) {
       net->step_graphs.push_back(fresh);
       sg = &net->step_graphs.back();
     } else {
       // replace, in ring order, an entry that never got a graph (a data set with more
       // batches than slots cycles through here and simply stays eager); recorded graphs
       // are never evicted by one-off keys
-      for (int tries = 0; tries < 32 && !sg; ++tries) {
-        pb_nnet::StepGraph *cand = &net->step_graphs[net->step_graph_next++ % 32];
+      for (size_t tries = 0; tries < kMaxStepGraphs && !sg; ++tries) {
+        pb_nnet::StepGraph *cand = &net->step_graphs[net->step_graph_next++ % kMaxStepGraphs];
         if (!cand->exec) sg = cand;
       }
       if (!sg) return body(user);
