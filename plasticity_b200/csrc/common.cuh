@@ -28,6 +28,11 @@ struct pb_context {
   std::vector<cudaStream_t> side_streams;
   // bumped whenever workspace / aux are reallocated: captured graphs hold their addresses
   uint64_t alloc_generation = 0;
+  // Programmatic dependent launch inside a fused training step (pb::launch_chained):
+  // 0 = plain launches; 1 = chained, the kernel's weights may still be being written by
+  // the launch before it; 2 = chained and the launch before it does not touch this
+  // kernel's weights (its weight prologue may run ahead of the dependency wait).
+  int chain = 0;
 };
 
 struct pb_nnet;
@@ -94,6 +99,41 @@ __device__ __forceinline__ float ref_exp(float x) {
       return pb::fail(std::string("kernel launch: ") +                       \
                       cudaGetErrorString(e__));                              \
   } while (0)
+
+namespace pb {
+
+// Programmatic dependent launch (griddepcontrol).  A kernel launched through
+// launch_chained with ctx->chain != 0 may START while the kernel queued before it is
+// still running; it must execute chain_wait() before it touches anything an earlier
+// kernel of the stream wrote (or writes anything an earlier kernel reads).  Every chained
+// kernel calls chain_wait() and only then chain_release(), so at most the next kernel's
+// prologue overlaps the running one and everything two launches back is complete and
+// visible.  Launched the ordinary way both instructions are no-ops.
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void chain_release() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(pb_context *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block,
+                                  size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  if (ctx->chain) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ctx->chain = 2;  // whatever follows is no longer the first launch of the step
+  }
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+}  // namespace pb
 
 static inline int pb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

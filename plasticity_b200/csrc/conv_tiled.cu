@@ -381,6 +381,8 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float *__restrict__ partial, int n_partial, int nw, const float *Wt,
                     float *out, const float *__restrict__ lr, int mode) {
   __shared__ float red[8][33];
+  chain_wait();  // chained launch, common.cuh
+  chain_release();
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int w = blockIdx.x * 32 + lane;
   float s0 = 0.0f, s1 = 0.0f;
@@ -404,8 +406,8 @@ wgrad_reduce_kernel(const float *__restrict__ partial, int n_partial, int nw, co
 
 int reduce_partials_update(pb_context *ctx, const float *partial, int n_partial, int nw,
                            const float *Wt, float *out, const float *lr, int mode) {
-  wgrad_reduce_kernel<<<pb_div_up(nw, 32), 256, 0, ctx->stream>>>(partial, n_partial, nw, Wt, out,
-                                                                  lr, mode);
+  PB_CUDA(launch_chained(ctx, wgrad_reduce_kernel, dim3(pb_div_up(nw, 32)), dim3(256), 0, partial,
+                         n_partial, nw, Wt, out, lr, mode));
   PB_LAUNCHED(ctx);
   return 0;
 }

@@ -143,7 +143,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float *bias_
 template <class C, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
-                 float *__restrict__ Out, float *__restrict__ Out2, int batch) {
+                 float *__restrict__ Out, float *__restrict__ Out2, int batch, int early_w) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float4 *a_s = reinterpret_cast<float4 *>(smem_raw);         // [2][A_STAGE]
   float4 *b_s = a_s + 2 * C::A_STAGE;                         // [B_UNITS]
@@ -163,6 +163,9 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   // is built from shared memory.
   constexpr int NWT = (C::BWD ? C::IC : C::OC) * K1;
   static_assert(NWT <= 8 * C::A_STAGE, "weight scratch must fit the A stages");
+  // Chained launch (common.cuh): when the launch before this one does not write this
+  // layer's filters, the whole setup runs while that kernel is still finishing.
+  if (!early_w) chain_wait();
   float *w_raw = reinterpret_cast<float *>(a_s);
   for (int i = tid; i < NWT; i += blockDim.x) w_raw[i] = Wt[i];
   __syncthreads();
@@ -214,6 +217,8 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int n_items = batch * C::IPS;
+  if (early_w) chain_wait();
+  chain_release();
 
   if (warp > kMmaWarp) {
     // ---- producers: global CHW -> [chunk][pixel][4] hi / lo ----------------
@@ -390,7 +395,9 @@ int launch_umma(pb_context *ctx, const float *In, const float *Wt, float *Out, i
   }
   const int64_t n_items = batch * C::IPS;
   const int grid = (int)std::min<int64_t>(n_items, ctx->num_sms);
-  kern<<<grid, kThreads, C::SMEM, ctx->stream>>>(In, Wt, Out, Out2, (int)batch);
+  const int early_w = ctx->chain == 2;
+  PB_CUDA(launch_chained(ctx, kern, dim3(grid), dim3(kThreads), C::SMEM, In, Wt, Out, Out2,
+                         (int)batch, early_w));
   PB_LAUNCHED(ctx);
   return 0;
 }

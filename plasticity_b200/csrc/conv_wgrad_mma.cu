@@ -95,6 +95,8 @@ conv_wgrad_mma_kernel(const float *__restrict__ In, const float *__restrict__ G,
   // zero once: halos, the channel planes past IC and the filter planes past OC stay zero
   for (int i = tid; i < C::MAIN_ELEMS; i += kThreads) smem[i] = 0.0f;
   __syncthreads();
+  chain_wait();  // chained launch (common.cuh): the zero fill above ran ahead of it
+  chain_release();
 
   const int b0 = blockIdx.x * samples_per_cta;
   const int b1 = min(batch, b0 + samples_per_cta);
@@ -242,6 +244,8 @@ __global__ void wgrad_mma_reduce_kernel(const float *__restrict__ partial, int n
   // block = 32 slots x 8 row groups: warp j sums partial rows j, j+8, ... of its 32 slots,
   // then the eight sums are added in order (deterministic)
   __shared__ float red[8][32];
+  chain_wait();
+  chain_release();
   const int lane_ = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int slot = blockIdx.x * 32 + lane_;
   float part = 0.0f;
@@ -287,10 +291,11 @@ int launch(pb_context *ctx, const float *I, const float *Wt, const float *G, flo
   const int spc = (batch + n_cta - 1) / n_cta;
   const int grid = (batch + spc - 1) / spc;
   if (ensure_workspace(ctx, (size_t)grid * C::ROW)) return 1;
-  kern<<<grid, kThreads, C::SMEM, ctx->stream>>>(I, G, ctx->workspace, batch, spc);
+  PB_CUDA(launch_chained(ctx, kern, dim3(grid), dim3(kThreads), C::SMEM, I, G, ctx->workspace,
+                         batch, spc));
   PB_LAUNCHED(ctx);
-  wgrad_mma_reduce_kernel<C><<<pb_div_up(C::ROW, 32), 256, 0, ctx->stream>>>(
-      ctx->workspace, grid, Wt, out, lr, mode);
+  PB_CUDA(launch_chained(ctx, wgrad_mma_reduce_kernel<C>, dim3(pb_div_up(C::ROW, 32)), dim3(256), 0,
+                         ctx->workspace, grid, Wt, out, lr, mode));
   PB_LAUNCHED(ctx);
   return 0;
 }
@@ -344,6 +349,8 @@ conv_wgrad_mma_rgb_kernel(const float *__restrict__ In, const float *__restrict_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  chain_wait();  // chained launch (common.cuh): zero fill and barrier setup ran ahead of it
+  chain_release();
   const int b0 = blockIdx.x * samples_per_cta;
   const int b1 = min(batch, b0 + samples_per_cta);
 
@@ -488,6 +495,8 @@ __global__ void wgrad_mma_rgb_reduce_kernel(const float *__restrict__ partial, i
                                             const float *Wt, float *out,
                                             const float *__restrict__ lr, int mode) {
   __shared__ float red[8][32];
+  chain_wait();
+  chain_release();
   const int lane_ = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int slot = blockIdx.x * 32 + lane_;
   float part = 0.0f;
@@ -530,10 +539,11 @@ int launch_rgb(pb_context *ctx, const float *I, const float *Wt, const float *G,
   const int spc = (batch + n_cta - 1) / n_cta;
   const int grid = (batch + spc - 1) / spc;
   if (ensure_workspace(ctx, (size_t)grid * C::ROW)) return 1;
-  kern<<<grid, C::THREADS + 32, C::SMEM, ctx->stream>>>(I, G, ctx->workspace, batch, spc);
+  PB_CUDA(launch_chained(ctx, kern, dim3(grid), dim3(C::THREADS + 32), C::SMEM, I, G,
+                         ctx->workspace, batch, spc));
   PB_LAUNCHED(ctx);
-  wgrad_mma_rgb_reduce_kernel<C><<<pb_div_up(C::ROW, 32), 256, 0, ctx->stream>>>(
-      ctx->workspace, grid, Wt, out, lr, mode);
+  PB_CUDA(launch_chained(ctx, wgrad_mma_rgb_reduce_kernel<C>, dim3(pb_div_up(C::ROW, 32)), dim3(256),
+                         0, ctx->workspace, grid, Wt, out, lr, mode));
   PB_LAUNCHED(ctx);
   return 0;
 }

@@ -242,6 +242,8 @@ int pool_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *I,
 template <int ACT>
 __global__ void act_pool_bwd_kernel(const float *__restrict__ O, const float *__restrict__ Gp,
                                     float *__restrict__ dO, int W, int H, int64_t total) {
+  chain_wait();  // chained launch, common.cuh
+  chain_release();
   const int wq = W >> 2, oh = H >> 1, ow = W >> 1;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -283,13 +285,15 @@ int act_pool_input_delta(pb_context *ctx, int act, const pb_layer_desc *pool, co
   const int64_t total = batch * pool->depth * (H / 2) * (W / 4);
   if (total == 0) return 0;
   const int grid = pb_ew_grid(ctx, total, 256);
+  cudaError_t err = cudaSuccess;
   switch (act) {
-    case PB_IDENTITY: act_pool_bwd_kernel<PB_IDENTITY><<<grid, 256, 0, ctx->stream>>>(O, Gp, dO, W, H, total); break;
-    case PB_RELU: act_pool_bwd_kernel<PB_RELU><<<grid, 256, 0, ctx->stream>>>(O, Gp, dO, W, H, total); break;
-    case PB_LEAKY_RELU: act_pool_bwd_kernel<PB_LEAKY_RELU><<<grid, 256, 0, ctx->stream>>>(O, Gp, dO, W, H, total); break;
-    case PB_SIGMOID: act_pool_bwd_kernel<PB_SIGMOID><<<grid, 256, 0, ctx->stream>>>(O, Gp, dO, W, H, total); break;
+    case PB_IDENTITY: err = launch_chained(ctx, act_pool_bwd_kernel<PB_IDENTITY>, dim3(grid), dim3(256), 0, O, Gp, dO, W, H, total); break;
+    case PB_RELU: err = launch_chained(ctx, act_pool_bwd_kernel<PB_RELU>, dim3(grid), dim3(256), 0, O, Gp, dO, W, H, total); break;
+    case PB_LEAKY_RELU: err = launch_chained(ctx, act_pool_bwd_kernel<PB_LEAKY_RELU>, dim3(grid), dim3(256), 0, O, Gp, dO, W, H, total); break;
+    case PB_SIGMOID: err = launch_chained(ctx, act_pool_bwd_kernel<PB_SIGMOID>, dim3(grid), dim3(256), 0, O, Gp, dO, W, H, total); break;
     default: return -1;
   }
+  PB_CUDA(err);
   PB_LAUNCHED(ctx);
   return 0;
 }

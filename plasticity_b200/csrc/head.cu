@@ -30,11 +30,15 @@ template <int ACT, int LOSS>
 __global__ void __launch_bounds__(256)
 head_kernel(const float *__restrict__ X, const float *__restrict__ W, const float *__restrict__ E,
             float *__restrict__ Z, float *__restrict__ A, float *__restrict__ Y,
-            float *__restrict__ Gz, float *__restrict__ dX, int in, int out, int64_t batch) {
+            float *__restrict__ Gz, float *__restrict__ dX, int in, int out, int64_t batch,
+            int early_w) {
   extern __shared__ float w_s[];  // [out][in+1], reference layout
   const int ld = in + 1;
+  if (!early_w) chain_wait();  // chained launch, common.cuh
   for (int i = threadIdx.x; i < out * ld; i += blockDim.x) w_s[i] = W[i];
   __syncthreads();
+  if (early_w) chain_wait();
+  chain_release();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -95,6 +99,8 @@ dense_wgrad_skinny_kernel(const float *__restrict__ X, const float *__restrict__
                           float *__restrict__ partial, int in, int out, int64_t batch,
                           int64_t per_split) {
   __shared__ float red[8][OUT][33];
+  chain_wait();
+  chain_release();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const int ld = in + 1;
@@ -128,14 +134,17 @@ int launch_head(pb_context *ctx, int loss, const float *X, const float *W, const
                 float *A, float *Y, float *Gz, float *dX, int in, int out, int64_t batch) {
   const size_t smem = sizeof(float) * (size_t)out * (in + 1);
   const int grid = (int)std::min<int64_t>((batch + 7) / 8, (int64_t)ctx->num_sms * 2);
+  const int early_w = ctx->chain == 2;
   if (loss == PB_MEAN_SQUARED) {
     auto k = head_kernel<ACT, PB_MEAN_SQUARED>;
     if (smem > 48 * 1024) PB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, ctx->stream>>>(X, W, E, Z, A, Y, Gz, dX, in, out, batch);
+    PB_CUDA(launch_chained(ctx, k, dim3(grid), dim3(256), smem, X, W, E, Z, A, Y, Gz, dX, in, out,
+                           batch, early_w));
   } else {
     auto k = head_kernel<ACT, PB_CROSS_ENTROPY>;
     if (smem > 48 * 1024) PB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, ctx->stream>>>(X, W, E, Z, A, Y, Gz, dX, in, out, batch);
+    PB_CUDA(launch_chained(ctx, k, dim3(grid), dim3(256), smem, X, W, E, Z, A, Y, Gz, dX, in, out,
+                           batch, early_w));
   }
   PB_LAUNCHED(ctx);
   return 0;
@@ -173,8 +182,8 @@ int dense_weight_update_skinny(pb_context *ctx, const pb_layer_desc *l, const fl
   splits = (int)((batch + per_split - 1) / per_split);
   if (ensure_workspace(ctx, (size_t)splits * nw)) return 1;
   dim3 grid(col_tiles, splits);
-  dense_wgrad_skinny_kernel<16><<<grid, 256, 0, ctx->stream>>>(X, G, ctx->workspace, (int)in,
-                                                                (int)nout, batch, per_split);
+  PB_CUDA(launch_chained(ctx, dense_wgrad_skinny_kernel<16>, grid, dim3(256), 0, X, G,
+                         ctx->workspace, (int)in, (int)nout, batch, per_split));
   PB_LAUNCHED(ctx);
   return reduce_partials_update(ctx, ctx->workspace, splits, (int)nw, W, out, lr, mode);
 }

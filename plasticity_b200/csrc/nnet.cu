@@ -677,8 +677,26 @@ int pb_nnet_train_loop(pb_nnet *net, const float *d_ins, const float *d_expected
 // grad_b, CalculateGradients); in_place == true (one chunk only): every layer's weight
 // kernel writes W - lr * sum_b grad_b straight into W — BatchTrain without the delta
 // round trip (nnet.h:652-665 VectorAccumulate fused into the weight kernels).
+static int batch_pass_body(pb_nnet *net, const float *d_ins, const float *d_expected,
+                           int64_t batch, bool in_place);
+
 static int batch_pass(pb_nnet *net, const float *d_ins, const float *d_expected, int64_t batch,
                       bool in_place) {
+  // The in-place single-chunk step launches its kernels chained (programmatic dependent
+  // launch, common.cuh): each kernel's setup — filters into shared memory, TMEM allocation,
+  // zero fills — overlaps the tail of the kernel before it.  PB_STEP_CHAIN=0 turns it off.
+  static const bool chain_on = [] {
+    const char *e = getenv("PB_STEP_CHAIN");
+    return !(e && e[0] == '0');
+  }();
+  net->ctx->chain = (chain_on && in_place && net->fuse && !net->profiling) ? 1 : 0;
+  const int rc = batch_pass_body(net, d_ins, d_expected, batch, in_place);
+  net->ctx->chain = 0;
+  return rc;
+}
+
+static int batch_pass_body(pb_nnet *net, const float *d_ins, const float *d_expected,
+                           int64_t batch, bool in_place) {
   pb_context *ctx = net->ctx;
   const int64_t nin = net->ni[0], nout = net->no.back();
   // Batches larger than max_batch run as chunks; every chunk sees the same
