@@ -42,18 +42,46 @@ head_kernel(const float *__restrict__ X, const float *__restrict__ W, const floa
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int KX = 8;  // inputs per lane and pass: a pass covers 32 * KX inputs
   for (int64_t b = warp; b < batch; b += nwarps) {
     const float *x = X + b * in;
-    // dense forward: lane o ends up holding z[o]
-    float z = 0.0f;
-    for (int o = 0; o < out; ++o) {
-      const float *w = w_s + o * ld;
-      float acc = 0.0f;
-      for (int i = lane; i < in; i += 32) acc = fmaf(w[i], x[i], acc);
-      acc = wsum(acc);
-      if (lane == o) z = w[in] + acc;
+    // dense forward.  Every lane keeps a partial sum per output over its own inputs (the
+    // loads of a pass are issued together, the outputs' FMA chains are independent), then a
+    // halving exchange leaves the total of output o in lane o: 31 shuffles for all outputs
+    // instead of five per output.
+    float acc[32];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) acc[o] = 0.0f;
+    for (int c0 = 0; c0 < in; c0 += 32 * KX) {
+      float xr[KX];
+      int ic[KX];
+#pragma unroll
+      for (int k = 0; k < KX; ++k) {
+        const int i = c0 + 32 * k + lane;
+        ic[k] = i < in ? i : in - 1;
+        xr[k] = i < in ? x[i] : 0.0f;
+      }
+#pragma unroll
+      for (int o = 0; o < 32; ++o) {
+        if (o < out) {
+          const float *w = w_s + o * ld;
+#pragma unroll
+          for (int k = 0; k < KX; ++k) acc[o] = fmaf(w[ic[k]], xr[k], acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+      const bool up = (lane & h) != 0;
+#pragma unroll
+      for (int j = 0; j < h; ++j) {
+        const float keep = up ? acc[j + h] : acc[j];
+        const float give = up ? acc[j] : acc[j + h];
+        acc[j] = keep + __shfl_xor_sync(0xffffffffu, give, h);
+      }
     }
     const bool on = lane < out;
+    const float z = on ? w_s[lane * ld + in] + acc[0] : 0.0f;
     const float a = act_fwd<ACT>(z);
     // softmax forward (e == 2.71828, max-shifted, ascending-lane sum order irrelevant at 1e-4)
     const float m = wmax(on ? a : -INFINITY);
@@ -80,13 +108,32 @@ head_kernel(const float *__restrict__ X, const float *__restrict__ W, const floa
       Y[b * out + lane] = y;
       Gz[b * out + lane] = gz;
     }
-    // dense input gradient: dX[i] = sum_o gz[o] * W[o][i]
-    for (int i0 = 0; i0 < in; i0 += 32) {  // uniform trip count: shuffles inside
-      const int i = i0 + lane;
-      const int ic = i < in ? i : in - 1;
-      float acc = 0.0f;
-      for (int o = 0; o < out; ++o) acc = fmaf(__shfl_sync(0xffffffffu, gz, o), w_s[o * ld + ic], acc);
-      if (i < in) dX[b * in + i] = acc;
+    // dense input gradient: dX[i] = sum_o gz[o] * W[o][i], ascending o; gz is broadcast to
+    // registers once (acc is free again)
+#pragma unroll
+    for (int o = 0; o < 32; ++o) acc[o] = __shfl_sync(0xffffffffu, gz, o);
+    for (int c0 = 0; c0 < in; c0 += 32 * KX) {
+      float d[KX];
+      int ic[KX];
+#pragma unroll
+      for (int k = 0; k < KX; ++k) {
+        const int i = c0 + 32 * k + lane;
+        ic[k] = i < in ? i : in - 1;
+        d[k] = 0.0f;
+      }
+#pragma unroll
+      for (int o = 0; o < 32; ++o) {
+        if (o < out) {
+          const float *w = w_s + o * ld;
+#pragma unroll
+          for (int k = 0; k < KX; ++k) d[k] = fmaf(acc[o], w[ic[k]], d[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KX; ++k) {
+        const int i = c0 + 32 * k + lane;
+        if (i < in) dX[b * in + i] = d[k];
+      }
     }
   }
 }

@@ -135,3 +135,43 @@ def test_wide_classifier_head(ctx):
     net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), B)
     got = util.read_product_weights(net, S)
     util.assert_close(got - w0, w_ref - w0, "wide head deltas", rtol=2e-4, atol_scale=2e-5)
+
+
+@pytest.mark.parametrize("n_in,n_out,act,loss", [
+    (333, 32, "sigmoid", "mse"),   # every lane owns an output; input tail inside a pass
+    (600, 17, "relu", "ce"),       # three passes of 256 inputs, odd output count
+    (64, 16, "leaky", "ce"),
+    (7, 5, "identity", "mse"),     # fewer inputs than lanes
+])
+def test_fused_head_shapes(ctx, n_in, n_out, act, loss):
+    """dense -> activation -> softmax + loss in the fused head kernel (head.cu: partial sums
+    per lane, halving exchange across the warp, gradients broadcast from registers) for
+    output counts up to a full warp and input counts off the 32-lane grid: three
+    gradient-sum steps against the oracle."""
+    B = 70
+    spec = (f"loss {loss}\nact {n_in} identity\ndense {n_in} {n_out}\nact {n_out} {act}\n"
+            f"softmax {n_out}\n")
+    S = po.RestatedNet(spec)
+    model, loss_fn = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(n_in * 37 + n_out)
+    w0 = util.xavier_like(S, rng)
+    # softmax behind a bounded activation under MSE has tiny gradients: a learning rate that
+    # keeps the updates well above one fp32 ulp of the weights they are added to
+    lr = 0.25 if loss == "mse" else 2e-3
+    net = pb.Nnet(model, pb.NoWeightInit, loss_fn, max_batch=B)
+    net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+    util.load_product_weights(net, S, w0)
+    w_ref = w0.copy()
+    for step in range(3):
+        xs = util.f32(rng.normal(0, 1, (B, n_in)))
+        es = np.zeros((B, n_out))
+        es[np.arange(B), rng.integers(0, n_out, B)] = 1.0
+        w_before = w_ref.copy()
+        S.batch_train(xs.copy(), es.copy(), w_ref, lr)
+        net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), B)
+        got = util.read_product_weights(net, S)
+        util.assert_close(got - w_before, w_ref - w_before, f"head step {step} deltas",
+                          rtol=2e-4, atol_scale=2e-5)
+        util.assert_close(got, w_ref, f"head step {step} weights")
+        # keep the two trajectories from drifting apart through fp32 rounding
+        util.load_product_weights(net, S, w_ref)
