@@ -233,6 +233,26 @@ conv_wgrad_mma_kernel(const float *__restrict__ In, const float *__restrict__ G,
     for (int nt = 0; nt < C::NT; ++nt) out[C::FRAG_ELEMS + nt * 8 + g] = bias_acc[nt];
 }
 
+// partial[p][slot] summed over p = grp, grp + 8, ... in ascending order.  One partial row
+// per CTA of the gradient kernel (at most one per SM): the first 20 terms — all of them up
+// to 160 rows — are loaded before the first addition, so the thread waits for one L2 round
+// trip instead of one per unrolled group.
+__device__ __forceinline__ float sum_partial_rows(const float *__restrict__ partial, int n_partial,
+                                                  int row_len, int slot, int grp) {
+  constexpr int kAhead = 20;
+  float v[kAhead];
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) {
+    const int p = grp + 8 * k;
+    v[k] = p < n_partial ? partial[(int64_t)p * row_len + slot] : 0.0f;
+  }
+  float part = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) part += v[k];
+  for (int p = grp + 8 * kAhead; p < n_partial; p += 8) part += partial[(int64_t)p * row_len + slot];
+  return part;
+}
+
 // Fixed-order sum of the per-CTA partials + the SGD update, one thread per FRAGMENT
 // slot (coalesced reads of every partial row; one scattered write per weight at the end).
 // D fragment: slot i of lane (g,t) is row g + 8*(i>>1), column 2t + (i&1); row = input
@@ -248,11 +268,7 @@ __global__ void wgrad_mma_reduce_kernel(const float *__restrict__ partial, int n
   chain_release();
   const int lane_ = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int slot = blockIdx.x * 32 + lane_;
-  float part = 0.0f;
-  if (slot < C::ROW) {
-#pragma unroll 4
-    for (int p = grp; p < n_partial; p += 8) part += partial[(int64_t)p * C::ROW + slot];
-  }
+  const float part = slot < C::ROW ? sum_partial_rows(partial, n_partial, C::ROW, slot, grp) : 0.0f;
   red[grp][lane_] = part;
   __syncthreads();
   if (grp != 0 || slot >= C::ROW) return;
@@ -499,11 +515,7 @@ __global__ void wgrad_mma_rgb_reduce_kernel(const float *__restrict__ partial, i
   chain_release();
   const int lane_ = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int slot = blockIdx.x * 32 + lane_;
-  float part = 0.0f;
-  if (slot < C::ROW) {
-#pragma unroll 4
-    for (int p = grp; p < n_partial; p += 8) part += partial[(int64_t)p * C::ROW + slot];
-  }
+  const float part = slot < C::ROW ? sum_partial_rows(partial, n_partial, C::ROW, slot, grp) : 0.0f;
   red[grp][lane_] = part;
   __syncthreads();
   if (grp != 0 || slot >= C::ROW) return;
