@@ -167,7 +167,9 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   // layer's filters, the whole setup runs while that kernel is still finishing.
   if (!early_w) chain_wait();
   float *w_raw = reinterpret_cast<float *>(a_s);
-  for (int i = tid; i < NWT; i += blockDim.x) w_raw[i] = Wt[i];
+  // L2 loads (ld.global.cg): ahead of the dependency wait nothing may rely on this SM's L1
+  // having been invalidated since the filters were last updated
+  for (int i = tid; i < NWT; i += blockDim.x) w_raw[i] = __ldcg(Wt + i);
   __syncthreads();
   for (int u = tid; u < C::B_UNITS; u += blockDim.x) {
     const int slot = u / C::N1, n = u - slot * C::N1;

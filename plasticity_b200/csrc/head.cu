@@ -35,7 +35,7 @@ head_kernel(const float *__restrict__ X, const float *__restrict__ W, const floa
   extern __shared__ float w_s[];  // [out][in+1], reference layout
   const int ld = in + 1;
   if (!early_w) chain_wait();  // chained launch, common.cuh
-  for (int i = threadIdx.x; i < out * ld; i += blockDim.x) w_s[i] = W[i];
+  for (int i = threadIdx.x; i < out * ld; i += blockDim.x) w_s[i] = __ldcg(W + i);  // L2: see conv_umma.cu
   __syncthreads();
   if (early_w) chain_wait();
   chain_release();
