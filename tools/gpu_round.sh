@@ -1,6 +1,6 @@
 #!/bin/bash
-# One gpurun call: parity tests, bench line, ncu launch list and full capture of
-# the convolution kernels.  Usage (from the repo root, on the GPU box):
+# One gpurun call: parity tests, chained-step race check, bench line, ncu launch list and
+# full capture of the convolution kernels.  Usage (from the repo root, on the GPU box):
 #   bash tools/gpu_round.sh <tag>
 set -u
 TAG=${1:-rXX}
@@ -9,6 +9,8 @@ mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1
 echo "pytest rc=$?" | tee -a $OUT/pytest_gpu_$TAG.log
 tail -3 $OUT/pytest_gpu_$TAG.log
+timeout 200 python tools/chain_check.py 100 1024 > $OUT/chain_check_$TAG.log 2>&1
+echo "chain_check rc=$?"; tail -1 $OUT/chain_check_$TAG.log
 python bench.py --steps 20 --warmup 3 --table $OUT/table_$TAG.json > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 echo "bench rc=$?"; cat $OUT/bench_$TAG.json
 BENCH_SHORT="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
