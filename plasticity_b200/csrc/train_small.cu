@@ -25,6 +25,8 @@ struct SmallNet {
   int w_off[kMaxLayers];    // offset of the layer's weights in the flat weight buffer
   int out_off[kMaxLayers];  // offset of the layer's outputs in the activation arena
   int total_w, total_out;
+  int wt_off[kMaxLayers];   // one-warp variant: offset of the layer's transposed weight block
+  int wt_total;
 };
 
 __device__ __forceinline__ float act_fwd_rt(int act, float x) {
@@ -150,6 +152,127 @@ train_small_kernel(const SmallNet net, float *__restrict__ W_global, const float
   for (int i = tid; i < net.total_w; i += kThreads) W_global[i] = W[i];
 }
 
+// ---- one-warp variant: every layer at most 32 values wide --------------------------------
+// Lane j owns value j of every layer, so a step needs no CTA barrier at all (__syncwarp
+// only).  Dense weights live in shared memory TRANSPOSED with pitch 33 —
+// wT[i * 33 + o] = W[o][i], row nin = the biases — so that both the forward product (fixed
+// input i, lanes = outputs) and the input gradient (fixed output o, lanes = inputs) read
+// conflict-free, and the activations of a layer are read as broadcasts.  The gradient vector
+// lives in one register per lane.  Same arithmetic and accumulation order as the kernel
+// above (ascending-index FMA chains; the softmax denominator is summed in ascending order
+// from the per-lane exponentials).
+constexpr int kWarpPitch = 33;
+
+__global__ void __launch_bounds__(32, 1)
+train_warp_kernel(const SmallNet net, float *__restrict__ W_global, const float *__restrict__ lr_p,
+                  const float *__restrict__ ins, const float *__restrict__ expected,
+                  long long n_samples) {
+  extern __shared__ float sm[];
+  float *acts = sm + net.wt_total;                 // [n_layers + 1][32]: acts[0] = the sample
+  float *gs = acts + (net.n_layers + 1) * 32;      // [32] broadcast buffer
+  const int lane = threadIdx.x;
+  for (int l = 0; l < net.n_layers; ++l) {
+    if (net.kind[l] != PB_DENSE) continue;
+    const int ld = net.nin[l] + 1;
+    for (int idx = lane; idx < net.nout[l] * ld; idx += 32) {
+      const int o = idx / ld, i = idx - o * ld;
+      sm[net.wt_off[l] + i * kWarpPitch + o] = W_global[net.w_off[l] + idx];
+    }
+  }
+  const float lr = lr_p[0];
+  float x_next = 0.0f, e_next = 0.0f;
+  if (n_samples > 0) {
+    if (lane < net.n_in) x_next = ins[lane];
+    if (lane < net.n_out) e_next = expected[lane];
+  }
+  __syncwarp();
+
+  for (long long s = 0; s < n_samples; ++s) {
+    if (lane < net.n_in) acts[lane] = x_next;
+    const float e_cur = e_next;
+    if (s + 1 < n_samples) {
+      if (lane < net.n_in) x_next = ins[(s + 1) * net.n_in + lane];
+      if (lane < net.n_out) e_next = expected[(s + 1) * net.n_out + lane];
+    }
+    __syncwarp();
+    // ---- forward ---------------------------------------------------------------
+    for (int l = 0; l < net.n_layers; ++l) {
+      const float *I = acts + l * 32;
+      float *O = acts + (l + 1) * 32;
+      const int nin = net.nin[l], nout = net.nout[l];
+      if (net.kind[l] == PB_ACTIVATION) {
+        if (lane < nout) O[lane] = act_fwd_rt(net.act[l], I[lane]);
+      } else if (net.kind[l] == PB_DENSE) {
+        if (lane < nout) {
+          const float *w = sm + net.wt_off[l] + lane;
+          float acc = w[nin * kWarpPitch];  // the accumulator starts at the bias
+          for (int i = 0; i < nin; ++i) acc = fmaf(w[i * kWarpPitch], I[i], acc);
+          O[lane] = acc;
+        }
+      } else {  // softmax
+        float m = lane < nin ? I[lane] : -INFINITY;
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float p = lane < nin ? ref_exp(I[lane] - m) : 0.0f;
+        gs[lane] = p;
+        __syncwarp();
+        float sum = 0.0f;
+        for (int i = 0; i < nin; ++i) sum += gs[i];
+        if (lane < nout) O[lane] = p / sum;
+      }
+      __syncwarp();
+    }
+    // ---- dE/dO (error_layer.cc:81-91): lane k holds the gradient of output k -----------
+    float g = 0.0f;
+    if (lane < net.n_out) {
+      const float o = acts[net.n_layers * 32 + lane];
+      g = net.loss == PB_MEAN_SQUARED ? o - e_cur : -1.0f * (e_cur * (1.0f / (o + kRefEps)));
+    }
+    // ---- reverse loop -----------------------------------------------------------
+    for (int l = net.n_layers - 1; l >= 0; --l) {
+      const float *I = acts + l * 32;
+      const int nin = net.nin[l], nout = net.nout[l];
+      if (net.kind[l] == PB_ACTIVATION) {
+        g = lane < nin ? act_bwd_rt(net.act[l], I[lane], g) : 0.0f;
+      } else if (net.kind[l] == PB_DENSE) {
+        gs[lane] = lane < nout ? g : 0.0f;
+        __syncwarp();
+        float ng = 0.0f;
+        if (lane < nin) {  // with the pre-update weights
+          const float *w = sm + net.wt_off[l] + lane * kWarpPitch;
+          for (int o = 0; o < nout; ++o) ng = fmaf(gs[o], w[o], ng);
+        }
+        __syncwarp();
+        if (lane < nout) {
+          float *w = sm + net.wt_off[l] + lane;
+          for (int i = 0; i < nin; ++i) w[i * kWarpPitch] = w[i * kWarpPitch] - lr * (g * I[i]);
+          w[nin * kWarpPitch] = w[nin * kWarpPitch] - lr * g;
+        }
+        g = ng;
+        __syncwarp();
+      } else {  // softmax: dI[k] = sum_i (O_i * (delta_ik - O_k)) * G_i, ascending i
+        const float *O = I + 32;
+        gs[lane] = lane < nout ? g : 0.0f;
+        __syncwarp();
+        float acc = 0.0f;
+        if (lane < nin) {
+          const float ok = O[lane];
+          for (int i = 0; i < nout; ++i) acc += (O[i] * (((i == lane) ? 1.0f : 0.0f) - ok)) * gs[i];
+        }
+        g = acc;
+        __syncwarp();
+      }
+    }
+  }
+  for (int l = 0; l < net.n_layers; ++l) {
+    if (net.kind[l] != PB_DENSE) continue;
+    const int ld = net.nin[l] + 1;
+    for (int idx = lane; idx < net.nout[l] * ld; idx += 32) {
+      const int o = idx / ld, i = idx - o * ld;
+      W_global[net.w_off[l] + idx] = sm[net.wt_off[l] + i * kWarpPitch + o];
+    }
+  }
+}
+
 }  // namespace
 
 // Returns -1 outside the envelope (layers other than activation / dense / softmax, more
@@ -168,7 +291,7 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
   net.n_layers = n_layers;
   net.loss = loss;
   net.total_w = (int)total_w;
-  int64_t out_total = 0, max_io = 1;
+  int64_t out_total = 0, max_io = 1, wt_total = 0;
   for (int l = 0; l < n_layers; ++l) {
     const pb_layer_desc &d = layers[l];
     int64_t a = 0, b = 0;
@@ -181,6 +304,8 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
     net.nout[l] = (int)b;
     net.w_off[l] = (int)w_off[l];
     net.out_off[l] = (int)out_total;
+    net.wt_off[l] = (int)wt_total;
+    if (d.kind == PB_DENSE) wt_total += (a + 1) * kWarpPitch;
     out_total += b;
     max_io = std::max(max_io, std::max(a, b));
   }
@@ -188,6 +313,25 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
   net.n_out = net.nout[n_layers - 1];
   net.max_io = (int)max_io;
   net.total_out = (int)out_total;
+  net.wt_total = (int)wt_total;
+  // PB_TRAIN_WARP=1: networks no wider than a warp run the one-warp kernel (opt-in until it
+  // has been through the GPU parity tests)
+  const char *warp_env = getenv("PB_TRAIN_WARP");
+  if (warp_env && warp_env[0] == '1' && max_io <= 32) {
+    const size_t wsmem = sizeof(float) * (size_t)(wt_total + (n_layers + 1) * 32 + 32);
+    if (wsmem <= 200 * 1024) {
+      static size_t wconfigured = 0;
+      if (wsmem > 48 * 1024 && wsmem > wconfigured) {
+        PB_CUDA(cudaFuncSetAttribute(train_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)wsmem));
+        wconfigured = wsmem;
+      }
+      train_warp_kernel<<<1, 32, wsmem, ctx->stream>>>(net, weights, lr, d_ins, d_expected,
+                                                       (long long)n_samples);
+      PB_LAUNCHED(ctx);
+      return 0;
+    }
+  }
   const size_t smem = sizeof(float) * (size_t)(total_w + net.n_in + out_total + 2 * max_io);
   if (smem > 200 * 1024) return -1;
   static size_t configured = 0;

@@ -437,3 +437,29 @@ def test_conv_weight_gradient_tensor_core_large_batch(ctx, layer, batch):
     L.call("pb_layer_weight_update", ctx, C.byref(desc), dI_.p, dW_.p, dG.p, dW_.p, d_lr.p,
            L.PB_NEW_WEIGHTS, batch)
     util.assert_close(dW_.host(), W + delta, f"layer {layer} in place")
+
+
+@pytest.mark.skipif(os.environ.get("PB_EXPERIMENTAL") != "1",
+                    reason="opt-in kernels that have not been through a GPU run yet (PB_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("name", ["circle", "mazur", "simple3", "relu3", "dense5"])
+def test_train_loop_one_warp_kernel(ctx, name, monkeypatch):
+    """PB_TRAIN_WARP=1: strict per-sample SGD of networks no wider than a warp in the one-warp
+    kernel (train_small.cu: lane j owns value j of every layer, transposed weights in shared
+    memory, no CTA barrier), 40 dependent steps against the oracle's Train loop."""
+    monkeypatch.setenv("PB_TRAIN_WARP", "1")
+    spec = po.spec_text(name)
+    S = po.RestatedNet(spec)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 5)
+    w0 = util.xavier_like(S, rng)
+    n = 40
+    xs = util.f32(rng.normal(0, 1, (n, S.n_in)))
+    es = util.f32(rng.uniform(0, 1, (n, S.n_out)))
+    lr = 0.05
+    net = pb.Nnet(model, pb.NoWeightInit, loss)
+    net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+    util.load_product_weights(net, S, w0)
+    w_ref = w0.copy()
+    S.train_loop(xs.copy(), es.copy(), w_ref, lr)
+    net.TrainLoop(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), n)
+    util.assert_close(util.read_product_weights(net, S), w_ref, f"{name} one-warp TrainLoop")
