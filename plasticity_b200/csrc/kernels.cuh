@@ -101,6 +101,12 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
                      const int64_t *w_off, int64_t total_w, int loss, float *weights,
                      const float *lr, const float *d_ins, const float *d_expected,
                      int64_t n_samples);
+// train_coop.cu: the same loop for any layer list as one cooperative persistent kernel
+// (opt-in, PB_TRAIN_COOP=1); -1 when not selected / outside its envelope
+int train_loop_coop(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
+                    const int64_t *w_off, int loss, float *weights, const float *lr,
+                    float *const *outputs, float *grad_a, float *grad_b, const float *d_ins,
+                    const float *d_expected, int64_t n_samples);
 
 // records.cu: pb_records_decode on an explicit stream.
 int records_decode_on(pb_context *ctx, cudaStream_t stream, const uint8_t *d_records,
@@ -150,6 +156,24 @@ __device__ __forceinline__ float act_bwd(float x, float g) {
     return g * (p / (q * q));
   }
   return g * 1.0f;
+}
+
+// The same with the activation kind as a run-time value (persistent per-sample kernels).
+__device__ __forceinline__ float act_fwd_rt(int act, float x) {
+  switch (act) {
+    case PB_RELU: return act_fwd<PB_RELU>(x);
+    case PB_LEAKY_RELU: return act_fwd<PB_LEAKY_RELU>(x);
+    case PB_SIGMOID: return act_fwd<PB_SIGMOID>(x);
+  }
+  return x;
+}
+__device__ __forceinline__ float act_bwd_rt(int act, float x, float g) {
+  switch (act) {
+    case PB_RELU: return act_bwd<PB_RELU>(x, g);
+    case PB_LEAKY_RELU: return act_bwd<PB_LEAKY_RELU>(x, g);
+    case PB_SIGMOID: return act_bwd<PB_SIGMOID>(x, g);
+  }
+  return act_bwd<PB_IDENTITY>(x, g);
 }
 
 }  // namespace pb

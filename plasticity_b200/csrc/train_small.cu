@@ -29,23 +29,6 @@ struct SmallNet {
   int wt_total;
 };
 
-__device__ __forceinline__ float act_fwd_rt(int act, float x) {
-  switch (act) {
-    case PB_RELU: return act_fwd<PB_RELU>(x);
-    case PB_LEAKY_RELU: return act_fwd<PB_LEAKY_RELU>(x);
-    case PB_SIGMOID: return act_fwd<PB_SIGMOID>(x);
-  }
-  return x;
-}
-__device__ __forceinline__ float act_bwd_rt(int act, float x, float g) {
-  switch (act) {
-    case PB_RELU: return act_bwd<PB_RELU>(x, g);
-    case PB_LEAKY_RELU: return act_bwd<PB_LEAKY_RELU>(x, g);
-    case PB_SIGMOID: return act_bwd<PB_SIGMOID>(x, g);
-  }
-  return act_bwd<PB_IDENTITY>(x, g);
-}
-
 __global__ void __launch_bounds__(kMaxThreads, 1)
 train_small_kernel(const SmallNet net, float *__restrict__ W_global, const float *__restrict__ lr_p,
                    const float *__restrict__ ins, const float *__restrict__ expected,
@@ -282,10 +265,8 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
                      const int64_t *w_off, int64_t total_w, int loss, float *weights,
                      const float *lr, const float *d_ins, const float *d_expected,
                      int64_t n_samples) {
-  static const bool off = [] {
-    const char *e = getenv("PB_TRAIN_SMALL");
-    return e && e[0] == '0';
-  }();
+  const char *small_env = getenv("PB_TRAIN_SMALL");  // read per call: one getenv per loop
+  const bool off = small_env && small_env[0] == '0';
   if (off || n_layers > kMaxLayers || n_layers < 1 || total_w > (1 << 16)) return -1;
   SmallNet net{};
   net.n_layers = n_layers;

@@ -463,3 +463,31 @@ def test_train_loop_one_warp_kernel(ctx, name, monkeypatch):
     S.train_loop(xs.copy(), es.copy(), w_ref, lr)
     net.TrainLoop(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), n)
     util.assert_close(util.read_product_weights(net, S), w_ref, f"{name} one-warp TrainLoop")
+
+
+@pytest.mark.skipif(os.environ.get("PB_EXPERIMENTAL") != "1",
+                    reason="opt-in kernels that have not been through a GPU run yet (PB_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("name", SPECS)
+def test_train_loop_cooperative_kernel(ctx, name, monkeypatch):
+    """PB_TRAIN_COOP=1: strict per-sample SGD of any layer list as one cooperative persistent
+    kernel (train_coop.cu: grid-stride phases separated by grid barriers), 12 dependent
+    steps against the oracle's Train loop."""
+    monkeypatch.setenv("PB_TRAIN_COOP", "1")
+    monkeypatch.setenv("PB_TRAIN_SMALL", "0")
+    spec = po.spec_text(name)
+    S = po.RestatedNet(spec)
+    R = checker(name)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 17)
+    w0 = util.xavier_like(S, rng)
+    n = 12
+    xs = util.f32(rng.normal(0, 1, (n, S.n_in)))
+    es = util.f32(rng.uniform(0, 1, (n, S.n_out)))
+    lr = 0.02
+    net = pb.Nnet(model, pb.NoWeightInit, loss)
+    net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+    util.load_product_weights(net, S, w0)
+    w_ref = w0.copy()
+    R.train_loop(xs.copy(), es.copy(), w_ref, lr)
+    net.TrainLoop(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), n)
+    util.assert_close(util.read_product_weights(net, S), w_ref, f"{name} cooperative TrainLoop")
