@@ -117,6 +117,13 @@ class Layer {
   size_t bp_train_workgroup_size() const { return CalculateWorkgroupSize(GetDimensions().num_inputs); }
 
   std::string LayerSuffix() const { return type_ + "_" + std::to_string(index_); }  // layer.h:99-101
+  // Kernel names of the reference's generated program (layer.h:91-114): what a
+  // compute::CommandQueue is asked to launch (compute/cuda_command_queue.h parses them).
+  const std::string &layer_type() const { return type_; }
+  std::string EvaluateKernelName() const { return "evaluate_" + std::to_string(index_); }
+  std::string InputGradientKernelName() const { return "input_delta_" + LayerSuffix(); }
+  std::string WeightUpdateKernelName() const { return "new_weights_" + LayerSuffix(); }
+  std::string WeightGradientKernelName() const { return "weight_delta_" + LayerSuffix(); }
   const pb_layer_desc &desc() const { return desc_; }
   size_t layer_index() const { return index_; }
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <set>
 
+#include "compute/cuda_command_queue.h"
 #include "nnet/nnet.h"
 #include "nnet/yolov1.h"
 
@@ -164,7 +165,104 @@ static void WorkgroupSizes() {
   EXPECT_TRUE(model.layers[1].bp_train_workgroup_size() == 32);       // 3072 inputs
 }
 
+// compute::CommandQueue (compute/command_queue.h:7-11) over CUDA: the reference's kernel
+// names + positional buffers reproduce Nnet::Evaluate and one Nnet::Train step of the
+// 2-2-2 sigmoid / MSE network (nnet_test.cc:194-274), launch by launch in nnet.h's order.
+static void KernelQueue() {
+  Architecture model(2);
+  model.AddDenseLayer(2, symbolic::Sigmoid);
+  model.AddDenseLayer(2, symbolic::Sigmoid);
+  DenseSymbolGenerator s(Dimensions{2, 2});
+  const double w1[2][3] = {{0.15, 0.2, 0.35}, {0.25, 0.3, 0.35}};
+  const double w3[2][3] = {{0.4, 0.45, 0.6}, {0.5, 0.55, 0.6}};
+  for (int o = 0; o < 2; ++o) {
+    for (int i = 0; i < 2; ++i) {
+      model.layers[1].W(s.WeightNumber(o, i)) = w1[o][i];
+      model.layers[3].W(s.WeightNumber(o, i)) = w3[o][i];
+    }
+    model.layers[1].W(s.WeightNumber(o)) = w1[o][2];
+    model.layers[3].W(s.WeightNumber(o)) = w3[o][2];
+  }
+  Nnet net(model, Nnet::NoWeightInit, MeanSquared);
+  net.SetLearningParameters(Nnet::LearningParameters{0.5});
+  pb_context *ctx = net.context();
+  std::vector<pb_layer_desc> descs;
+  std::vector<std::string> types;
+  for (auto &l : model.layers) {
+    descs.push_back(l.desc());
+    types.push_back(l.layer_type());
+  }
+  compute::CudaCommandQueue queue(ctx, descs, types, PB_MEAN_SQUARED);
+  const size_t n = model.layers.size();
+  // per-layer device buffers: outputs, weights, gradients
+  std::vector<compute::ClBuffer> out(n), W(n);
+  compute::ClBuffer in(std::vector<double>{0.05, 0.1}), expected(std::vector<double>{0.01, 0.99});
+  compute::ClBuffer lr(std::vector<double>{0.5});
+  for (compute::ClBuffer *b : {&in, &expected, &lr}) b->RegisterClBackend(ctx);
+  for (size_t l = 0; l < n; ++l) {
+    out[l] = compute::ClBuffer(model.layers[l].GetDimensions().num_outputs, ctx);
+    out[l].MoveToGpu();
+    model.layers[l].weight_buffer().MoveToCpu();
+    W[l] = compute::ClBuffer(model.layers[l].weight_buffer());  // private copy of the weights
+    W[l].RegisterClBackend(ctx);
+  }
+  auto args = [](std::initializer_list<compute::ClBuffer *> bufs) {
+    auto v = std::make_unique<std::vector<compute::ClBuffer>>(bufs.size());
+    size_t k = 0;
+    for (compute::ClBuffer *b : bufs) (*v)[k++] = *b;  // operator= aliases the device handle
+    return v;
+  };
+  // forward, nnet.h:234-268
+  for (size_t l = 0; l < n; ++l) {
+    compute::ClBuffer &I = l ? out[l - 1] : in;
+    queue.enqueueKernel(model.layers[l].EvaluateKernelName(),
+                        (int)model.layers[l].GetDimensions().num_outputs,
+                        (int)model.layers[l].eval_workgroup_size(), args({&I, &W[l], &out[l]}));
+  }
+  queue.finish();
+  auto net_in = net.MakeBuffer({0.05, 0.1});
+  auto net_expected = net.MakeBuffer({0.01, 0.99});
+  auto want = net.Evaluate(net_in);
+  want->MoveToCpu();
+  compute::ClBuffer got(out[n - 1]);  // device copy, then read back
+  got.MoveToCpu();
+  EXPECT_NEAR(got[0], want->at(0), 1e-6);
+  EXPECT_NEAR(got[1], want->at(1), 1e-6);
+  EXPECT_NEAR(got[0], 0.75136507, 1e-5);
+  // error gradients + reverse loop, nnet.h:316-349, 399-460
+  compute::ClBuffer g(2, ctx), ng(2, ctx);
+  g.MoveToGpu();
+  ng.MoveToGpu();
+  queue.enqueueKernel("error_gradients", 2, 2, args({&out[n - 1], &expected, &g}));
+  for (size_t l = n; l-- > 0;) {
+    Layer &L = model.layers[l];
+    compute::ClBuffer &I = l ? out[l - 1] : in;
+    queue.enqueueKernel(L.InputGradientKernelName(), (int)L.GetDimensions().num_inputs,
+                        (int)L.bp_train_workgroup_size(), args({&I, &W[l], &g, &ng}));
+    if (W[l].size() > 0) {
+      compute::ClBuffer new_w(W[l].size(), ctx);
+      new_w.MoveToGpu();
+      queue.enqueueKernel(L.WeightUpdateKernelName(), (int)W[l].size(),
+                          (int)L.weight_train_workgroup_size(), args({&I, &W[l], &g, &new_w, &lr}));
+      W[l] = new_w;  // handle swap, nnet.h:454
+    }
+    compute::ClBuffer t;
+    t = g; g = ng; ng = t;
+  }
+  queue.finish();
+  net.Train(net_in, net_expected);
+  for (size_t l : {size_t(1), size_t(3)}) {
+    compute::ClBuffer mine(W[l]);
+    mine.MoveToCpu();
+    for (size_t k = 0; k < mine.size(); ++k) EXPECT_NEAR(mine[k], net.GetWeight(l, k), 1e-6);
+  }
+  compute::ClBuffer w3_new(W[3]);
+  w3_new.MoveToCpu();
+  EXPECT_NEAR(w3_new[s.WeightNumber(0, 0)], 0.35891648, 1e-5);  // nnet_test.cc:260-273
+}
+
 int main() {
+  if (std::getenv("PB_EXPERIMENTAL")) KernelQueue();  // written without a GPU: opt-in until run
   WorkgroupSizes();
   Yolo();
   OneLayerRelu();

@@ -12,6 +12,7 @@ OUT=gpurun_out; mkdir -p $OUT
 PB_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q \
     -k "cooperative or one_warp" > $OUT/experimental_$TAG.log 2>&1
 echo "experimental tests rc=$?"; grep -E "^E  |passed|failed" $OUT/experimental_$TAG.log | cut -c1-220 | tail -15
+(cd tests/cpp && PB_EXPERIMENTAL=1 timeout 120 ./mirror_test | tail -3)   # + compute::CudaCommandQueue case
 for w in 0 1; do
   PB_TRAIN_WARP=$w timeout 120 python tools/bench_circle.py > $OUT/circle_${TAG}_warp$w.json 2> $OUT/circle_${TAG}_warp$w.err
   echo "circle PB_TRAIN_WARP=$w rc=$?: $(tail -1 $OUT/circle_${TAG}_warp$w.json | cut -c1-160)"
