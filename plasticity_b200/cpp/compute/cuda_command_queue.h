@@ -4,7 +4,7 @@
 //   evaluate_<i>(I, W, O)                         global = outputs of layer i
 //   input_delta_<type>_<i>(I, W, G, dI)           global = inputs  of layer i
 //   new_weights_<type>_<i>(I, W, G, Wnew, lr)     global = weights of layer i
-//   weight_delta_<type>_<i>(I, W, G, dW, lr)      global = weights of layer i
+//   weight_delta[s]_<type>_<i>(I, W, G, dW, lr)   global = weights of layer i
 //   error_value(O, E, e)   error_gradients(O, E, G)   vector_accumulate(a, b)
 // There is no program to look the name up in: the name is parsed and the launch goes to the
 // layer-type launcher of include/plasticity_b200.h with layer i's dimensions.  The
@@ -61,8 +61,10 @@ class CudaCommandQueue : public CommandQueue {
       return;
     }
     struct Form { const char *prefix; int kind; };
+    // the kernel template is called weight_deltas_* (back_prop.kernel.cl:37-44), the host
+    // asks for weight_delta_* (nnet/layer.h:112-114): both spellings are accepted
     static const Form forms[] = {{"evaluate_", 0}, {"input_delta_", 1}, {"new_weights_", 2},
-                                 {"weight_delta_", 3}};
+                                 {"weight_delta_", 3}, {"weight_deltas_", 3}};
     for (const Form &f : forms) {
       const std::string prefix(f.prefix);
       if (kernel_name.compare(0, prefix.size(), prefix) != 0) continue;
