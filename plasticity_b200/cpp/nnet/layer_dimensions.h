@@ -3,6 +3,7 @@
 #define PLASTICITY_B200_LAYER_DIMENSIONS_H_
 
 #include <cstddef>
+#include <initializer_list>
 
 namespace nnet {
 

@@ -227,3 +227,22 @@ def test_bench_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "cifar_cnn_batch_train"
+
+
+def test_cpp_mirror_headers_compile_standalone(tmp_path):
+    """Every header of the C++ host mirror (plasticity_b200/cpp: the reference's include
+    paths — nnet/*.h, compute/cl_buffer.h, compute/command_queue.h + the CUDA command queue)
+    compiles on its own with the host compiler: a reference-side caller needs nothing but
+    -I<repo>/plasticity_b200/cpp -I<repo>/include."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cpp = os.path.join(root, "plasticity_b200", "cpp")
+    headers = sorted(os.path.relpath(os.path.join(d, f), cpp)
+                     for d, _, fs in os.walk(cpp) for f in fs if f.endswith(".h"))
+    assert "compute/command_queue.h" in headers and "nnet/nnet.h" in headers
+    for h in headers:
+        tu = tmp_path / "tu.cc"
+        tu.write_text(f'#include "{h}"\nint main() {{ return 0; }}\n')
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-I", cpp,
+                            "-I", os.path.join(root, "include"), str(tu)],
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, f"{h} does not compile on its own:\n{r.stderr[-1500:]}"
