@@ -246,3 +246,15 @@ def test_cpp_mirror_headers_compile_standalone(tmp_path):
                             "-I", os.path.join(root, "include"), str(tu)],
                            capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, f"{h} does not compile on its own:\n{r.stderr[-1500:]}"
+
+
+def test_abi_header_is_plain_c(tmp_path):
+    """include/plasticity_b200.h is the drop-in boundary: it must compile as plain C (no C++,
+    no CUDA, no torch types) so that cgo / JNI / ctypes-style bindings can consume it."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tu = tmp_path / "abi.c"
+    tu.write_text('#include "plasticity_b200.h"\nint main(void) { return pb_abi_version() < 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I",
+                        os.path.join(root, "include"), str(tu)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr[-2000:]
