@@ -230,7 +230,9 @@ int conv_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
                        int mode, int64_t batch) {
   if (conv_check(l)) return 1;
   if (batch >= kTiledMinBatch) {
-    int rc = conv_weight_update_mma(ctx, l, I, W, G, out, lr, mode, batch);
+    int rc = conv_weight_update_umma(ctx, l, I, W, G, out, lr, mode, batch);
+    if (rc >= 0) return rc;
+    rc = conv_weight_update_mma(ctx, l, I, W, G, out, lr, mode, batch);
     if (rc >= 0) return rc;
     rc = conv_weight_update_tiled(ctx, l, I, W, G, out, lr, mode, batch);
     if (rc >= 0) return rc;

@@ -76,6 +76,11 @@ int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const floa
 int conv_weight_update_mma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *Wt,
                            const float *G, float *out, const float *lr, int mode, int64_t batch);
 
+// conv_wgrad_umma.cu: 3xTF32 tcgen05 weight gradient (gradient operand in tensor memory) for
+// the same layers; tried first, -1 outside the envelope.
+int conv_weight_update_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *Wt,
+                            const float *G, float *out, const float *lr, int mode, int64_t batch);
+
 // conv_umma.cu: 3xTF32 tcgen05 implicit-GEMM kernels for the batched CIFAR
 // shapes; return -1 outside their envelope.
 int conv_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,

@@ -33,7 +33,7 @@ for l in layers:
             fn(); fn()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for _ in range(10): fn()
+            for _ in range(int(os.environ.get("REPS", "10"))): fn()
             e1.record(stream); e1.synchronize()
-            print(f"layer {l} {kind} B={B}: {e0.elapsed_time(e1)/10*1000:.1f} us", flush=True)
+            print(f"layer {l} {kind} B={B}: {e0.elapsed_time(e1)/int(os.environ.get("REPS", "10"))*1000:.1f} us", flush=True)
         for p in (I, O, G, dI, W, out): L.call("pb_buffer_free", ctx, p)
