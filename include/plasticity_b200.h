@@ -245,9 +245,18 @@ typedef struct pb_comm pb_comm;
 int pb_comm_unique_id(void *id_bytes /* PB_COMM_ID_BYTES */);
 int pb_comm_create(pb_context *ctx, const void *id_bytes, int rank, int n_ranks,
                    pb_comm **comm);
+/* n_ranks communicators inside ONE process (contexts on the same or on different devices),
+ * no NCCL: rank r of the group is comms[r].  The ranks' steps are queued from one host thread,
+ * rank after rank, and meet on the device; supports the peer-memory exchange of networks up
+ * to 2^20 weights.  What the multi-rank parity test uses on a single-GPU box (ranks that share
+ * a device wait for each other ON the device: run with CUDA_DEVICE_MAX_CONNECTIONS >= the
+ * number of streams in use so that no two of them share a hardware queue). */
+int pb_comm_create_local(pb_context *const *ctxs, int n_ranks, pb_comm **comms /* [n_ranks] */);
 int pb_comm_destroy(pb_comm *comm);
 int pb_comm_allreduce_sum(pb_comm *comm, float *d_buf, int64_t n);
-/* pb_nnet_batch_gradients + all-reduce of the deltas + pb_nnet_apply_deltas. */
+/* The data-parallel gradient-sum step on this rank's shard: pb_nnet_batch_gradients, the
+ * exchange of the summed deltas and the update, W += sum over ranks, bit-identical on every
+ * rank.  Fails (and keeps failing) once a peer did not arrive within 5 s. */
 int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
                            const float *d_expected, int64_t local_batch);
 

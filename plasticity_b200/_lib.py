@@ -86,6 +86,7 @@ SIGNATURES = {
     "pb_nnet_batch_train": [_vp, _vp, _vp, C.c_int64],
     "pb_comm_unique_id": [_vp],
     "pb_comm_create": [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)],
+    "pb_comm_create_local": [C.POINTER(_vp), C.c_int, C.POINTER(_vp)],
     "pb_comm_destroy": [_vp],
     "pb_comm_allreduce_sum": [_vp, _vp, C.c_int64],
     "pb_nnet_batch_train_dp": [_vp, _vp, _vp, _vp, C.c_int64],

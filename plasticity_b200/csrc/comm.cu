@@ -7,13 +7,13 @@
 //
 // For small networks (the CIFAR net has 22 466 weights = 90 KB) the all-reduce is
 // pure latency, so the exchange and the weight update are ONE kernel over NVLink
-// peer memory (p2p_allreduce_apply_kernel): every rank pushes its delta buffer
-// into an inbox slot on every peer with remote stores, publishes a flag, waits
+// peer memory behind the gradient pass (p2p_inbox_kernel): every rank pushes its delta
+// buffer into an inbox slot on every peer with remote stores, publishes a flag, waits
 // for the peers' flags and adds the contributions in rank order (bit-identical
 // weights on all ranks) straight into W.  Inboxes are double-buffered by step
 // parity; peer memory is mapped with CUDA IPC handles exchanged through NCCL at
-// the first step.  Large delta buffers (the 4096-wide MLP) keep the bandwidth-
-// optimal ncclAllReduce + accumulate path.
+// the first step.  Large delta buffers (the 4096-wide MLP) exchange layer by layer,
+// overlapped with the backward pass (p2p_bucket_kernel), or through ncclAllReduce.
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,23 +26,33 @@
 
 constexpr int kMaxP2pRanks = 8;
 constexpr int64_t kMaxP2pFloats = 1 << 20;   // above this the exchange is bandwidth-bound: NCCL
-constexpr size_t kP2pHeader = 256;           // bytes reserved for the flag words
+constexpr int kXCtas = 16;                   // CTAs of the small exchange kernel (one flag set each)
+constexpr size_t kP2pHeader = 2048;          // bytes reserved for the flag words [2][kXCtas][ranks]
 constexpr int kMaxBuckets = 256;             // layers of a network (one exchange bucket each)
 // flag block of the large exchange, uint32 words:
 //   [bucket][phase A|B][source rank]  then  [bucket] CTA-arrival counters
 constexpr size_t kBigFlagWords = (size_t)kMaxBuckets * 2 * kMaxP2pRanks + kMaxBuckets;
 
+struct pb_comm;
+// ranks living in one process (pb_comm_create_local): plain device pointers instead of IPC
+struct pb_local_group {
+  std::vector<pb_comm *> members;
+  int alive = 0;
+};
+
 struct pb_comm {
   pb_context *ctx = nullptr;
+  pb_local_group *group = nullptr;
   ncclComm_t comm = nullptr;
   int rank = 0, n_ranks = 1;
+  int id = 0;                   // process-wide serial: recorded step graphs are keyed on it
   // peer-memory exchange block: [flags[2][kMaxP2pRanks] | inbox[2][n_ranks][p2p_n]]
   int p2p_state = 0;            // 0 = not tried, 1 = ready, -1 = unavailable (NCCL fallback)
   int64_t p2p_n = 0;
   void *local = nullptr;
   void *peers[kMaxP2pRanks] = {nullptr};
-  uint32_t epoch = 0;
-  int *d_timeout = nullptr;     // set by the kernel if a peer never showed up
+  uint32_t *d_xepoch = nullptr; // [kXCtas] step counters of the small exchange, bumped by its CTAs
+  int *d_timeout = nullptr;     // = ctx->fault (mapped host word): a peer never showed up
   // large delta buffers: per-layer all-reduce on a second stream, overlapped with the
   // rest of the backward pass (last layer first)
   cudaStream_t comm_stream = nullptr;
@@ -111,54 +121,106 @@ struct P2pPeers {
   uint32_t *flags[kMaxP2pRanks];   // peer r's flag words
 };
 
-// One CTA.  n is a multiple of 4; all buffers 16-byte aligned.
-__global__ void __launch_bounds__(1024)
-p2p_allreduce_apply_kernel(P2pPeers peers, const float *__restrict__ deltas, float *W, int64_t n,
-                           int rank, int n_ranks, uint32_t epoch, int *timeout_flag) {
-  const int slot = epoch & 1;
-  const int64_t n4 = n >> 2;
-  const float4 *src = reinterpret_cast<const float4 *>(deltas);
-  // push my contribution into slot [slot][rank] of every rank's inbox (mine included)
-  for (int r = 0; r < n_ranks; ++r) {
-    float4 *dst = reinterpret_cast<float4 *>(peers.inbox[r] + ((int64_t)slot * n_ranks + rank) * n);
-    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < n_ranks) {
-    // publish, then wait for every peer's flag of this step
-    volatile uint32_t *theirs = peers.flags[threadIdx.x] + slot * kMaxP2pRanks + rank;
-    *theirs = epoch + 1;
-    volatile uint32_t *mine = peers.flags[rank] + slot * kMaxP2pRanks + threadIdx.x;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while ((int)(*mine - (epoch + 1)) < 0) {
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 5000000000ull) {  // 5 s: a rank is missing; do not hang the GPU
-        *timeout_flag = 1;
-        break;
-      }
+// Waits until *word reaches `epoch`; false (and *fault raised) after 5 s: a rank is missing.
+__device__ __forceinline__ bool spin_until(volatile uint32_t *word, uint32_t epoch, int *fault) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((int)(*word - epoch) < 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 5000000000ull) {
+      *(volatile int *)fault = 1;
+      __threadfence_system();
+      return false;
     }
   }
+  return true;
+}
+
+// The exchange step of a small network as ONE kernel, launched chained right behind the
+// gradient pass on the compute stream.  kXCtas CTAs; CTA c owns slice c of the flat buffer:
+//   push   its slice of this rank's deltas into slot [step parity][rank] of EVERY rank's
+//          inbox (remote stores over NVLink, posted);
+//   flag   one word per (parity, CTA, source rank) on every rank, then wait for the R words
+//          of this CTA on this rank - the only latency-bound point of the step;
+//   apply  W[slice] += contributions in rank order, read from the local inbox: every rank
+//          forms the identical sum, so the weights stay bit-identical with no second barrier
+//          and no all-gather.  A rank cannot run two steps ahead of a peer (its next flag
+//          wait needs that peer's next flag), so two inbox slots suffice.
+// A missing peer raises *fault and the CTA leaves W untouched.
+__global__ void __launch_bounds__(256)
+p2p_inbox_kernel(P2pPeers peers, const float *__restrict__ deltas, float *W, int64_t n, int rank,
+                 int n_ranks, uint32_t *epoch_c, int *fault) {
+  // No early chain_release(): a successor made resident now would sit on its shared memory
+  // until every peer has arrived - fatal when several ranks share one device.
+  chain_wait();
+  const int c = blockIdx.x;
+  const uint32_t epoch = epoch_c[c];
+  const int slot = epoch & 1;
+  const int64_t n4 = n >> 2;
+  const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = c * per, i1 = min(n4, i0 + per);
+  const float4 *src = reinterpret_cast<const float4 *>(deltas);
+  for (int r = 0; r < n_ranks; ++r) {
+    float4 *dst = reinterpret_cast<float4 *>(peers.inbox[r] + ((int64_t)slot * n_ranks + rank) * n);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = src[i];
+  }
   __threadfence_system();
   __syncthreads();
+  int ok = 1;
+  if (threadIdx.x < n_ranks) {
+    const size_t word = ((size_t)slot * kXCtas + c) * kMaxP2pRanks;
+    *(volatile uint32_t *)(peers.flags[threadIdx.x] + word + rank) = epoch + 1;
+    ok = spin_until(peers.flags[rank] + word + threadIdx.x, epoch + 1, fault);
+  }
+  __threadfence_system();
+  if (!__syncthreads_and(ok)) return;
   const float4 *in = reinterpret_cast<const float4 *>(peers.inbox[rank] + (int64_t)slot * n_ranks * n);
   float4 *w4 = reinterpret_cast<float4 *>(W);
-  for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < n_ranks; ++r) {  // rank order: identical sums everywhere
-      const float4 v = in[(int64_t)r * n4 + i];
+      const float4 v = __ldcg(in + (int64_t)r * n4 + i);  // written by a peer: not through L1
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     float4 w = w4[i];
     w.x += acc.x; w.y += acc.y; w.z += acc.z; w.w += acc.w;
     w4[i] = w;
   }
+  if (threadIdx.x == 0) epoch_c[c] = epoch + 1;
 }
 
 // Collective: every rank calls it at the same point.  Returns 0 and sets
 // comm->p2p_state to 1 (ready) or -1 (all ranks fall back to NCCL).
 static int p2p_setup(pb_comm *c, int64_t n) {
+  if (c->group) {
+    // in-process ranks: the first rank to get here allocates every member's block
+    const size_t bytes = kP2pHeader + sizeof(float) * (size_t)(2 * c->n_ranks * n);
+    int dev0 = 0;
+    PB_CUDA(cudaGetDevice(&dev0));
+    for (pb_comm *m : c->group->members) {
+      PB_CUDA(cudaSetDevice(m->ctx->device));
+      PB_CUDA(cudaMalloc(&m->local, bytes));
+      PB_CUDA(cudaMemset(m->local, 0, bytes));
+      PB_CUDA(cudaMalloc((void **)&m->d_xepoch, sizeof(uint32_t) * kXCtas));
+      PB_CUDA(cudaMemset(m->d_xepoch, 0, sizeof(uint32_t) * kXCtas));
+      if (ensure_fault_word(m->ctx)) return 1;
+      m->d_timeout = m->ctx->fault;
+      for (pb_comm *o : c->group->members)
+        if (o->ctx->device != m->ctx->device) {
+          const cudaError_t e = cudaDeviceEnablePeerAccess(o->ctx->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+          cudaGetLastError();
+        }
+    }
+    for (pb_comm *m : c->group->members) {
+      for (int r = 0; r < c->n_ranks; ++r) m->peers[r] = c->group->members[r]->local;
+      m->p2p_state = 1;
+      m->p2p_n = n;
+    }
+    PB_CUDA(cudaSetDevice(dev0));
+    return 0;
+  }
   NcclApi *api = nccl_api();
   c->p2p_state = -1;
   if (!api || !api->AllGather || c->n_ranks > kMaxP2pRanks || (n & 3)) return 0;
@@ -171,8 +233,10 @@ static int p2p_setup(pb_comm *c, int64_t n) {
   if (ok && cudaMalloc(&c->local, bytes) != cudaSuccess) { ok = 0; c->local = nullptr; }
   if (ok && cudaMemsetAsync(c->local, 0, bytes, st) != cudaSuccess) ok = 0;
   if (ok && cudaIpcGetMemHandle(&mine, c->local) != cudaSuccess) ok = 0;
-  if (cudaMalloc((void **)&c->d_timeout, sizeof(int)) != cudaSuccess) ok = 0;
-  else cudaMemsetAsync(c->d_timeout, 0, sizeof(int), st);
+  if (ensure_fault_word(c->ctx)) ok = 0;
+  c->d_timeout = c->ctx->fault;
+  if (ok && cudaMalloc((void **)&c->d_xepoch, sizeof(uint32_t) * kXCtas) != cudaSuccess) ok = 0;
+  if (ok && cudaMemsetAsync(c->d_xepoch, 0, sizeof(uint32_t) * kXCtas, st) != cudaSuccess) ok = 0;
   // exchange {ok, handle} with every rank (device-side all-gather through NCCL)
   struct Rec { int ok; int pad; cudaIpcMemHandle_t h; };
   Rec rec; rec.ok = ok; rec.pad = 0; rec.h = mine;
@@ -219,19 +283,6 @@ struct BigPeers {
   float *D[kMaxP2pRanks];
   uint32_t *flags[kMaxP2pRanks];
 };
-
-__device__ __forceinline__ bool spin_until(volatile uint32_t *word, uint32_t epoch, int *timeout_flag) {
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while ((int)(*word - epoch) < 0) {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 5000000000ull) {  // 5 s: a rank is missing; do not hang the GPU
-      *timeout_flag = 1;
-      return false;
-    }
-  }
-  return true;
-}
 
 // One bucket (= one layer's slice [off, off+n) of the flat weight / delta buffers) of the
 // data-parallel exchange, FUSED with the weight update, over NVLink peer memory:
@@ -285,6 +336,7 @@ __global__ void __launch_bounds__(128, 5)
 p2p_bucket_kernel(BigPeers P, int64_t off, int64_t n, int bucket, int rank, int R,
                   const uint32_t *epoch_p, int *timeout_flag) {
   const uint32_t epoch = *epoch_p;
+  int arrived = 1;
   uint32_t *mine = P.flags[rank] + (size_t)bucket * 2 * kMaxP2pRanks;
   uint32_t *counter = P.flags[rank] + (size_t)kMaxBuckets * 2 * kMaxP2pRanks + bucket;
   if (threadIdx.x < R) {
@@ -292,9 +344,10 @@ p2p_bucket_kernel(BigPeers P, int64_t off, int64_t n, int bucket, int rank, int 
       __threadfence_system();
       *(volatile uint32_t *)(P.flags[threadIdx.x] + (size_t)bucket * 2 * kMaxP2pRanks + rank) = epoch;
     }
-    spin_until(mine + threadIdx.x, epoch, timeout_flag);
+    if (!spin_until(mine + threadIdx.x, epoch, timeout_flag)) arrived = 0;
   }
-  __syncthreads();
+  // a missing peer: leave W untouched (the raised fault word fails the next host call)
+  if (!__syncthreads_and(arrived)) return;
   const int64_t n4 = n >> 2;
   const int64_t per = (n4 + R - 1) / R;
   const int64_t s0 = (int64_t)rank * per, s1 = min(n4, s0 + per);
@@ -347,10 +400,8 @@ static int big_setup(pb_comm *c, float *weights, float *deltas, int n_layers) {
   if (ok && cudaIpcGetMemHandle(&rec.d, deltas) != cudaSuccess) ok = 0;
   if (ok && cudaIpcGetMemHandle(&rec.f, c->big_local_flags) != cudaSuccess) ok = 0;
   if (!ok) cudaGetLastError();
-  if (!c->d_timeout) {
-    if (cudaMalloc((void **)&c->d_timeout, sizeof(int)) != cudaSuccess) ok = 0;
-    else cudaMemsetAsync(c->d_timeout, 0, sizeof(int), st);
-  }
+  if (ensure_fault_word(c->ctx)) ok = 0;
+  c->d_timeout = c->ctx->fault;
   rec.ok = ok;
   Rec *d_recs = nullptr;
   std::vector<Rec> recs((size_t)c->n_ranks);
@@ -476,6 +527,8 @@ int pb_comm_create(pb_context *ctx, const void *id_bytes, int rank, int n_ranks,
   memcpy(&id, id_bytes, sizeof(id));
   pb_comm *c = new pb_comm();
   c->ctx = ctx; c->rank = rank; c->n_ranks = n_ranks;
+  static int next_id = 0;
+  c->id = ++next_id;  // a graph recorded for a destroyed communicator is never replayed
   ncclResult_t r = api->CommInitRank(&c->comm, n_ranks, id, rank);
   if (r != ncclSuccess) {
     delete c;
@@ -486,8 +539,34 @@ int pb_comm_create(pb_context *ctx, const void *id_bytes, int rank, int n_ranks,
   return 0;
 }
 
+int pb_comm_create_local(pb_context *const *ctxs, int n_ranks, pb_comm **comms) {
+  PB_CHECK(ctxs && comms, "pb_comm_create_local: null");
+  PB_CHECK(n_ranks >= 1 && n_ranks <= kMaxP2pRanks, "pb_comm_create_local: 1..8 ranks");
+  pb_local_group *g = new pb_local_group();
+  static int next_local_id = 1 << 20;
+  for (int r = 0; r < n_ranks; ++r) {
+    PB_CHECK(ctxs[r], "pb_comm_create_local: null context");
+    pb_comm *c = new pb_comm();
+    c->ctx = ctxs[r]; c->rank = r; c->n_ranks = n_ranks; c->group = g;
+    c->id = ++next_local_id;
+    g->members.push_back(c);
+    comms[r] = c;
+  }
+  g->alive = n_ranks;
+  return 0;
+}
+
 int pb_comm_destroy(pb_comm *comm) {
   if (!comm) return 0;
+  if (comm->group) {
+    cudaSetDevice(comm->ctx->device);
+    cudaStreamSynchronize(comm->ctx->stream);
+    if (comm->local) cudaFree(comm->local);
+    if (comm->d_xepoch) cudaFree(comm->d_xepoch);
+    if (--comm->group->alive == 0) delete comm->group;
+    delete comm;
+    return 0;
+  }
   pb::NcclApi *api = pb::nccl_api();
   if (api && comm->comm) {
     cudaStreamSynchronize(comm->ctx->stream);
@@ -509,7 +588,7 @@ int pb_comm_destroy(pb_comm *comm) {
     if (comm->big_local_flags) cudaFree(comm->big_local_flags);
     if (comm->d_epoch) cudaFree(comm->d_epoch);
     if (comm->local) cudaFree(comm->local);
-    if (comm->d_timeout) cudaFree(comm->d_timeout);
+    if (comm->d_xepoch) cudaFree(comm->d_xepoch);
     api->CommDestroy(comm->comm);
   }
   delete comm;
@@ -519,6 +598,7 @@ int pb_comm_destroy(pb_comm *comm) {
 int pb_comm_allreduce_sum(pb_comm *comm, float *d_buf, int64_t n) {
   PB_CHECK(comm && (n == 0 || d_buf), "pb_comm_allreduce_sum: null");
   if (n == 0 || comm->n_ranks == 1) return 0;
+  PB_CHECK(!comm->group, "pb_comm_allreduce_sum: not available for in-process rank groups");
   pb::NcclApi *api = pb::nccl_api();
   PB_CHECK(api, "pb_comm_allreduce_sum: NCCL unavailable");
   PB_NCCL(api, api->AllReduce(d_buf, d_buf, (size_t)n, ncclFloat, ncclSum, comm->comm,
@@ -529,85 +609,92 @@ int pb_comm_allreduce_sum(pb_comm *comm, float *d_buf, int64_t n) {
 int pb_nnet_batch_train_dp(pb_nnet *net, pb_comm *comm, const float *d_ins,
                            const float *d_expected, int64_t local_batch) {
   PB_CHECK(net && comm, "pb_nnet_batch_train_dp: null");
-  float *deltas = nullptr;
+  if (pb::check_fault(comm->ctx)) return 1;
+  // one rank: exactly the single-GPU step (update fused into the weight-gradient kernels)
+  if (comm->n_ranks == 1) return pb_nnet_batch_train(net, d_ins, d_expected, local_batch);
+  float *deltas = nullptr, *W = nullptr;
   int64_t n = 0;
-  if (pb_nnet_deltas_device(net, &deltas) || pb_nnet_total_weights(net, &n)) return 1;
-  static const bool overlap = [] {
-    const char *e = getenv("PB_DP_OVERLAP");
-    return !(e && e[0] == '0');
-  }();
-  // PB_DP_BUCKETS=0: small delta buffers use the single-kernel inbox exchange after the pass
-  static const bool small_buckets = [] {
-    const char *e = getenv("PB_DP_BUCKETS");
-    return !(e && e[0] == '0');
-  }();
-  if (comm->n_ranks > 1 && overlap && (n > kMaxP2pFloats || small_buckets)) {
-    // One exchange per layer, started as soon as that layer's weight gradient is done —
-    // last layer first — on a high-priority second stream, so the exchange of layer l
-    // overlaps the backward kernels of layers l-1, l-2, ...: for the bandwidth-bound case
-    // (the 4096-wide MLP: 134 MB) and for the latency-bound one (the CIFAR net: 90 KB,
-    // where only the first layer's 5 KB bucket stays exposed) alike.
+  int32_t n_layers = 0;
+  if (pb_nnet_deltas_device(net, &deltas) || pb_nnet_total_weights(net, &n) ||
+      pb_nnet_weights_device(net, &W) || pb_nnet_num_layers(net, &n_layers))
+    return 1;
+  if (n <= kMaxP2pFloats) {
+    // Small network (the CIFAR net: 22 466 weights, 90 KB): the exchange is pure latency.
+    // The step is the chained gradient pass + ONE exchange-and-update kernel behind it on
+    // the same stream, recorded into a CUDA graph like the single-GPU step.
+    if (comm->p2p_state == 0 && pb::p2p_setup(comm, n)) return 1;
+    if (comm->p2p_state == 1 && comm->p2p_n == n) {
+      struct Body {
+        pb_nnet *net; pb_comm *comm; const float *ins, *exp; int64_t batch, n; float *W, *deltas;
+      } body{net, comm, d_ins, d_expected, local_batch, n, W, deltas};
+      auto run = [](void *u) -> int {
+        Body *b = (Body *)u;
+        pb_comm *c = b->comm;
+        if (pb_nnet_batch_gradients(b->net, b->ins, b->exp, b->batch)) return 1;
+        pb::P2pPeers peers;
+        for (int r = 0; r < kMaxP2pRanks; ++r) {
+          char *base = (char *)c->peers[r < c->n_ranks ? r : c->rank];
+          peers.flags[r] = (uint32_t *)base;
+          peers.inbox[r] = (float *)(base + kP2pHeader);
+        }
+        c->ctx->chain = c->ctx->chain_last ? 2 : 0;
+        const cudaError_t e = pb::launch_chained(c->ctx, pb::p2p_inbox_kernel, dim3(kXCtas), dim3(256),
+                                                 0, peers, b->deltas, b->W, b->n, c->rank,
+                                                 c->n_ranks, c->d_xepoch, c->d_timeout);
+        c->ctx->chain = 0;
+        PB_CUDA(e);
+        PB_LAUNCHED(c->ctx);
+        return 0;
+      };
+      return pb::nnet_run_graphed(net, d_ins, d_expected, local_batch, 2 + 4 * comm->id, run, &body);
+    }
+  } else {
+    PB_CHECK(!comm->group, "pb_nnet_batch_train_dp: in-process rank groups handle networks of "
+                           "up to 2^20 weights");
+    // Large delta buffers (the 4096-wide MLP: 134 MB, bandwidth-bound): one exchange per
+    // layer, started as soon as that layer's weight gradient is done - last layer first -
+    // on a high-priority second stream, so the exchange of layer l overlaps the backward
+    // kernels of layers l-1, l-2, ...
     if (!comm->comm_stream) {
       int lo = 0, hi = 0;
       PB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       PB_CUDA(cudaStreamCreateWithPriority(&comm->comm_stream, cudaStreamNonBlocking, hi));
     }
-    float *W = nullptr;
-    int32_t n_layers = 0;
-    if (pb_nnet_weights_device(net, &W) || pb_nnet_num_layers(net, &n_layers)) return 1;
     if (comm->big_state == 0 || (comm->big_state == 1 && comm->big_weights != W)) {
       PB_CHECK(comm->big_state == 0, "pb_nnet_batch_train_dp: one network per communicator");
       if (pb::big_setup(comm, W, deltas, n_layers)) return 1;
     }
     // peer-memory exchange fused with the update when every rank could map every rank;
-    // otherwise NCCL all-reduce + accumulate per layer (large buffers) or the paths below
+    // otherwise NCCL all-reduce + accumulate per layer on the same hook
     const bool p2p = comm->big_state == 1;
-    if (p2p || n > kMaxP2pFloats) {
-      struct Body {
-        pb_nnet *net; pb_comm *comm; const float *ins, *exp; int64_t batch; bool p2p;
-      } body{net, comm, d_ins, d_expected, local_batch, p2p};
-      auto run = [](void *u) -> int {
-        Body *b = (Body *)u;
-        pb_comm *c = b->comm;
-        c->events_used = 0;
-        if (b->p2p) {
-          pb::bump_epoch_kernel<<<1, 1, 0, c->ctx->stream>>>(c->d_epoch);
-          PB_LAUNCHED(c->ctx);
-        }
-        pb::nnet_set_delta_hook(b->net, b->p2p ? pb::p2p_bucket_hook : pb::overlap_hook, c);
-        const int rc = pb_nnet_batch_gradients(b->net, b->ins, b->exp, b->batch);
-        pb::nnet_set_delta_hook(b->net, nullptr, nullptr);
-        if (rc) return 1;
-        cudaEvent_t done = pb::next_event(c);
-        PB_CUDA(cudaEventRecord(done, c->comm_stream));
-        PB_CUDA(cudaStreamWaitEvent(c->ctx->stream, done, 0));
-        return 0;
-      };
-      // the peer-memory step is device-driven end to end (flags, step counter): it is
-      // recorded into a CUDA graph like the single-GPU step; the NCCL variant stays eager
-      if (p2p) return pb::nnet_run_graphed(net, d_ins, d_expected, local_batch, 1, run, &body);
-      return run(&body);
-    }
-  }
-  if (pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch)) return 1;
-  if (comm->n_ranks > 1 && n <= kMaxP2pFloats) {
-    if (comm->p2p_state == 0 && pb::p2p_setup(comm, n)) return 1;
-    if (comm->p2p_state == 1 && comm->p2p_n == n) {
-      float *W = nullptr;
-      if (pb_nnet_weights_device(net, &W)) return 1;
-      pb::P2pPeers peers;
-      for (int r = 0; r < kMaxP2pRanks; ++r) {
-        char *base = (char *)comm->peers[r < comm->n_ranks ? r : comm->rank];
-        peers.flags[r] = (uint32_t *)base;
-        peers.inbox[r] = (float *)(base + kP2pHeader);
+    struct Body {
+      pb_nnet *net; pb_comm *comm; const float *ins, *exp; int64_t batch; bool p2p;
+    } body{net, comm, d_ins, d_expected, local_batch, p2p};
+    auto run = [](void *u) -> int {
+      Body *b = (Body *)u;
+      pb_comm *c = b->comm;
+      c->events_used = 0;
+      if (b->p2p) {
+        pb::bump_epoch_kernel<<<1, 1, 0, c->ctx->stream>>>(c->d_epoch);
+        PB_LAUNCHED(c->ctx);
       }
-      pb::p2p_allreduce_apply_kernel<<<1, 1024, 0, comm->ctx->stream>>>(
-          peers, deltas, W, n, comm->rank, comm->n_ranks, comm->epoch, comm->d_timeout);
-      comm->epoch++;
-      PB_LAUNCHED(comm->ctx);
+      pb::nnet_set_delta_hook(b->net, b->p2p ? pb::p2p_bucket_hook : pb::overlap_hook, c);
+      const int rc = pb_nnet_batch_gradients(b->net, b->ins, b->exp, b->batch);
+      pb::nnet_set_delta_hook(b->net, nullptr, nullptr);
+      if (rc) return 1;
+      cudaEvent_t done = pb::next_event(c);
+      PB_CUDA(cudaEventRecord(done, c->comm_stream));
+      PB_CUDA(cudaStreamWaitEvent(c->ctx->stream, done, 0));
       return 0;
-    }
+    };
+    // the peer-memory step is device-driven end to end (flags, step counter): it is
+    // recorded into a CUDA graph like the single-GPU step; the NCCL variant stays eager
+    if (p2p) return pb::nnet_run_graphed(net, d_ins, d_expected, local_batch, 1 + 4 * comm->id, run, &body);
+    return run(&body);
   }
+  // no peer mapping (or PB_DISABLE_P2P=1): NCCL all-reduce of the delta buffer + accumulate
+  PB_CHECK(!comm->group, "pb_nnet_batch_train_dp: in-process rank group without peer access");
+  if (pb_nnet_batch_gradients(net, d_ins, d_expected, local_batch)) return 1;
   if (pb_comm_allreduce_sum(comm, deltas, n)) return 1;
   return pb_nnet_apply_deltas(net);
 }

@@ -33,6 +33,10 @@ struct pb_context {
   // the launch before it; 2 = chained and the launch before it does not touch this
   // kernel's weights (its weight prologue may run ahead of the dependency wait).
   int chain = 0;
+  bool chain_last = false;  // the gradient pass that just ran was launched chained
+  // Set (through a mapped pinned host word) by a data-parallel exchange kernel whose peer
+  // never arrived: the kernel skips its update and every later synchronising call fails.
+  int *fault = nullptr;
 };
 
 struct pb_nnet;
@@ -54,6 +58,9 @@ int fail(const std::string &msg);
 int ensure_stage(pb_context *ctx, size_t elems);
 int ensure_workspace(pb_context *ctx, size_t elems);
 int ensure_aux(pb_context *ctx, size_t elems);
+// non-zero (error set) once a data-parallel exchange kernel reported a missing peer
+int check_fault(pb_context *ctx);
+int ensure_fault_word(pb_context *ctx);
 
 // The reference prints NumericValue::e with 6 significant digits
 // (symbolic/numeric_value.cc:41-53), so its kernels compute pow(2.71828, x).

@@ -54,6 +54,21 @@ int ensure_aux(pb_context *ctx, size_t elems) {
   return 0;
 }
 
+int check_fault(pb_context *ctx) {
+  if (ctx->fault && *(volatile int *)ctx->fault)
+    return fail("data-parallel exchange: a peer rank did not arrive within 5 s; the weight "
+                "update of that step was skipped on this rank and training must stop");
+  return 0;
+}
+
+// Mapped pinned host word a kernel can raise without the host having to poll the device.
+int ensure_fault_word(pb_context *ctx) {
+  if (ctx->fault) return 0;
+  PB_CUDA(cudaHostAlloc((void **)&ctx->fault, sizeof(int), cudaHostAllocMapped));
+  *ctx->fault = 0;
+  return 0;
+}
+
 __global__ void f64_to_f32_kernel(const double *__restrict__ src,
                                   float *__restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -119,6 +134,7 @@ int pb_context_destroy(pb_context *ctx) {
   if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->workspace) cudaFree(ctx->workspace);
   if (ctx->aux) cudaFree(ctx->aux);
+  if (ctx->fault) cudaFreeHost(ctx->fault);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -128,7 +144,7 @@ int pb_context_finish(pb_context *ctx) {
   PB_CHECK(ctx, "pb_context_finish: null ctx");
   PB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (cudaStream_t st : ctx->side_streams) PB_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return pb::check_fault(ctx);
 }
 
 int pb_context_device(const pb_context *ctx, int *device) {
@@ -192,7 +208,7 @@ int pb_buffer_read_f64(pb_context *ctx, const float *src, double *host, size_t n
   PB_CUDA(cudaMemcpyAsync(host, ctx->stage, n * sizeof(double),
                           cudaMemcpyDeviceToHost, ctx->stream));
   PB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return pb::check_fault(ctx);
 }
 
 int pb_buffer_write_f32(pb_context *ctx, float *dst, const float *host, size_t n) {

@@ -693,15 +693,16 @@ static int batch_pass(pb_nnet *net, const float *d_ins, const float *d_expected,
   // The in-place single-chunk step launches its kernels chained (programmatic dependent
   // launch, common.cuh): each kernel's setup — filters into shared memory, TMEM allocation,
   // zero fills — overlaps the tail of the kernel before it.  PB_STEP_CHAIN=0 turns it off.
-  // PB_STEP_CHAIN=2 also chains the delta-buffer pass (chunked and data-parallel steps: the
-  // weights do not change inside the pass, the exchange kernels sit behind events on their
-  // own streams) — not the default until it has been through tools/dp_check.py on 2+ GPUs.
-  static const int chain_mode = [] {
+  // The delta-buffer pass (chunked and data-parallel steps) is chained too: the weights do
+  // not change inside the pass and the exchange kernels sit behind it (or behind events on
+  // their own stream).
+  static const bool chain_on = [] {
     const char *e = getenv("PB_STEP_CHAIN");
-    return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1;
+    return !(e && e[0] == '0');
   }();
-  const bool chain_on = chain_mode == 2 || (chain_mode == 1 && in_place);
+  (void)in_place;
   net->ctx->chain = (chain_on && net->fuse && !net->profiling) ? 1 : 0;
+  net->ctx->chain_last = net->ctx->chain != 0;
   const int rc = batch_pass_body(net, d_ins, d_expected, batch, in_place);
   net->ctx->chain = 0;
   return rc;

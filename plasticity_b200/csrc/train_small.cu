@@ -295,10 +295,8 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
   net.max_io = (int)max_io;
   net.total_out = (int)out_total;
   net.wt_total = (int)wt_total;
-  // PB_TRAIN_WARP=1: networks no wider than a warp run the one-warp kernel (opt-in until it
-  // has been through the GPU parity tests)
-  const char *warp_env = getenv("PB_TRAIN_WARP");
-  if (warp_env && warp_env[0] == '1' && max_io <= 32) {
+  // networks no wider than a warp run the one-warp kernel
+  if (max_io <= 32) {
     const size_t wsmem = sizeof(float) * (size_t)(wt_total + (n_layers + 1) * 32 + 32);
     if (wsmem <= 200 * 1024) {
       static size_t wconfigured = 0;

@@ -204,6 +204,22 @@ def context(device: int = 0):
     return _ctx_cache[device]
 
 
+def new_context(device: int = 0):
+    """A private pb_context (its own CUDA stream) on `device`: one per rank when several ranks
+    of a data-parallel group live in one process (pb_comm_create_local)."""
+    h = C.c_void_p()
+    L.call("pb_context_create", device, C.byref(h))
+    return h
+
+
+def local_comms(ctxs):
+    """pb_comm_create_local: one communicator per context, rank = position."""
+    arr = (C.c_void_p * len(ctxs))(*[c.value for c in ctxs])
+    out = (C.c_void_p * len(ctxs))()
+    L.call("pb_comm_create_local", arr, len(ctxs), out)
+    return [C.c_void_p(v) for v in out]
+
+
 class ClBuffer:
     """compute::ClBuffer: a float64 host vector OR an fp32 device allocation,
     with explicit MoveToGpu / MoveToCpu (blocking, like the reference)."""
@@ -315,7 +331,7 @@ class Nnet:
 
     def __init__(self, model: Architecture, weight_initialization: int = Xavier,
                  loss_function: int = MeanSquared, max_batch: int = 1, device: int = 0,
-                 seed: int = 0):
+                 seed: int = 0, ctx=None):
         if not model.VerifyArchitecture():
             raise L.PlasticityError("Invalid dimensions passed to Nnet()")  # nnet.h:55-59
         # The reference copies the Architecture (deep copy of every Layer and its
@@ -326,7 +342,7 @@ class Nnet:
             dst.weights[:] = src.weights
             self.model_.layers.append(dst)
         self.loss = loss_function
-        self.ctx = context(device)
+        self.ctx = ctx if ctx is not None else context(device)
         self.max_batch = max_batch
         descs = (L.LayerDesc * len(model.layers))(*[l.desc for l in model.layers])
         self.h = C.c_void_p()

@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# Several in-process ranks of a data-parallel group on ONE device (tests/test_gpu_dp.py) wait
+# for each other on the device: their streams must not share a hardware queue.  Must be set
+# before the first CUDA call of the process.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

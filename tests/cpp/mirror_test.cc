@@ -262,7 +262,7 @@ static void KernelQueue() {
 }
 
 int main() {
-  if (std::getenv("PB_EXPERIMENTAL")) KernelQueue();  // written without a GPU: opt-in until run
+  KernelQueue();
   WorkgroupSizes();
   Yolo();
   OneLayerRelu();

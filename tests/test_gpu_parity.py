@@ -439,14 +439,11 @@ def test_conv_weight_gradient_tensor_core_large_batch(ctx, layer, batch):
     util.assert_close(dW_.host(), W + delta, f"layer {layer} in place")
 
 
-@pytest.mark.skipif(os.environ.get("PB_EXPERIMENTAL") != "1",
-                    reason="opt-in kernels that have not been through a GPU run yet (PB_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("name", ["circle", "mazur", "simple3", "relu3", "dense5"])
 def test_train_loop_one_warp_kernel(ctx, name, monkeypatch):
-    """PB_TRAIN_WARP=1: strict per-sample SGD of networks no wider than a warp in the one-warp
-    kernel (train_small.cu: lane j owns value j of every layer, transposed weights in shared
-    memory, no CTA barrier), 40 dependent steps against the oracle's Train loop."""
-    monkeypatch.setenv("PB_TRAIN_WARP", "1")
+    """Strict per-sample SGD of networks no wider than a warp runs in the one-warp kernel
+    (train_small.cu: lane j owns value j of every layer, transposed weights in shared
+    memory, no CTA barrier): 40 dependent steps against the oracle's Train loop."""
     spec = po.spec_text(name)
     S = po.RestatedNet(spec)
     model, loss = util.architecture_from_spec(spec)
@@ -465,8 +462,6 @@ def test_train_loop_one_warp_kernel(ctx, name, monkeypatch):
     util.assert_close(util.read_product_weights(net, S), w_ref, f"{name} one-warp TrainLoop")
 
 
-@pytest.mark.skipif(os.environ.get("PB_EXPERIMENTAL") != "1",
-                    reason="opt-in kernels that have not been through a GPU run yet (PB_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("name", SPECS)
 def test_train_loop_cooperative_kernel(ctx, name, monkeypatch):
     """PB_TRAIN_COOP=1: strict per-sample SGD of any layer list as one cooperative persistent
