@@ -119,6 +119,13 @@ def reference_rate(np, steps, warmup, sample, threads_note=True):
     or the plain-C port when that build is absent.  Gradient-sum minibatch,
     examples spread over all host threads."""
     os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every host core
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:  # the OpenMP runtime may already be loaded (it reads the variable once)
+        C.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
     from oracle import pyoracle as po
     if po.RefNet.available("cifar"):
         net, kind = po.RefNet("cifar"), "reference"
@@ -137,7 +144,6 @@ def reference_rate(np, steps, warmup, sample, threads_note=True):
     for _ in range(steps):
         net.batch_train_mt(x, e, w, 1e-4)
     dt = time.perf_counter() - t0
-    cores = os.cpu_count() or 1
     return {"value": steps * sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{steps} steps x {sample} samples of the same workload "
                       f"(gradient-sum minibatch, OpenMP over examples, double precision)",
@@ -157,8 +163,11 @@ def run_reference(args):
         "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cifar_cnn_batch_train", "mode": "gradient_sum_minibatch",
-                   "batch_per_step": sample, "lr": 1e-4, "loss": "cross_entropy",
-                   "network": "nnet/cifar_test.cc:293-350 (13 layers, 22466 params)"},
+                   "batch_per_gpu": sample, "global_batch": sample, "lr": 1e-4,
+                   "loss": "cross_entropy",
+                   "network": "nnet/cifar_test.cc:293-350 (13 layers, 22466 params)",
+                   "note": "CPU arm: one host, every step = one gradient-sum minibatch of "
+                           "batch_per_gpu samples whatever --gpus says"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -296,6 +305,36 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed_blocks(step_fn, first_index, wall=False):
+        """The K-step block, bracketed by barrier + synchronize on both sides and timed with
+        CUDA events on the library stream (max over ranks), repeated until >= --min-seconds
+        of timed work: a 20-step block of this workload is ~6 ms, too short to be a
+        measurement on its own.  Returns the per-block times (ms)."""
+        out, idx = [], first_index
+        total = 0.0
+        while not out or (total < args.min_seconds * 1e3 and len(out) < args.max_blocks):
+            barrier()
+            ea = torch.cuda.Event(enable_timing=True)
+            eb = torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                step_fn(idx + i)
+            eb.record(stream)
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            dev_ms = ea.elapsed_time(eb)
+            blk = maxreduce(max(dev_ms, wall_ms) if wall else dev_ms)
+            # every rank takes the same decision: the reduced block time drives the loop
+            out.append(blk)
+            total += blk
+            idx += args.steps
+        return out
+
+    def median(v):
+        v = sorted(v)
+        return v[len(v) // 2] if len(v) % 2 else 0.5 * (v[len(v) // 2 - 1] + v[len(v) // 2])
+
     # ---------------- device-resident timing ------------------------------
     # Set-up, not warm-up: the library records the step for a given (inputs, targets)
     # pair into a CUDA graph on its second use; touch every resident batch twice so the
@@ -307,17 +346,11 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = launches()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    e0.record(stream)
-    for i in range(args.steps):
-        step_resident(args.warmup + i)
-    e1.record(stream)
-    barrier()
+    blocks = timed_blocks(step_resident, args.warmup)
     t_wall1 = time.time()
-    ms = maxreduce(e0.elapsed_time(e1))
-    n_launch = launches() - l0
+    ms = median(blocks)
+    n_launch = (launches() - l0) // len(blocks)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -345,17 +378,7 @@ def run_ours(args):
     def time_e2e(step_fn):
         for i in range(max(min(args.warmup, 3), 4)):  # both staging slots twice (graph capture)
             step_fn(i)
-        barrier()
-        e2 = torch.cuda.Event(enable_timing=True)
-        e3 = torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            step_fn(i)
-        e3.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        return maxreduce(max(e2.elapsed_time(e3), wall_ms))
+        return median(timed_blocks(step_fn, 0, wall=True))
 
     ms_e2e = time_e2e(step_e2e)
 
@@ -375,6 +398,92 @@ def run_ours(args):
 
     ms_e2e_fp32 = time_e2e(step_e2e_fp32)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---------------- data-parallel parity (N > 1), after the timed regions ---------------
+    dp_parity = None
+    if world > 1:
+        tw = C.c_int64()
+        L.call("pb_nnet_total_weights", net.h, C.byref(tw))
+        wp = C.c_void_p()
+        L.call("pb_nnet_weights_device", net.h, C.byref(wp))
+
+        def read_w():
+            h = np.zeros(tw.value, dtype=np.float32)
+            L.call("pb_buffer_read_f32", ctx, wp, h.ctypes.data, tw.value)
+            return h
+
+        barrier()
+        w_start = read_w()                       # identical on every rank (checked below)
+        for i in range(2):
+            step_resident(i)                      # two data-parallel steps on batches 0 and 1
+        barrier()
+        w_dp = read_w()
+        mine = torch.from_numpy(np.concatenate([w_start, w_dp])).cuda()
+        allw = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allw, mine)
+        identical = all(torch.equal(allw[0], a) for a in allw)
+        # the same two steps on ONE GPU over the global batch (rank 0)
+        xg = [torch.empty(2 * B * 3072, dtype=torch.float32, device="cuda") for _ in range(world)]
+        eg = [torch.empty(2 * B * 10, dtype=torch.float32, device="cuda") for _ in range(world)]
+        dist.all_gather(xg, torch.from_numpy(x[:2 * B].reshape(-1)).cuda())
+        dist.all_gather(eg, torch.from_numpy(e[:2 * B].reshape(-1)).cuda())
+        if rank == 0:
+            one = pb.Nnet(model, pb.NoWeightInit, pb.CrossEntropy, max_batch=world * B, device=local)
+            one.SetLearningParameters(pb.Nnet.LearningParameters(1e-4))
+            one._sync_to_device()
+            wp1 = C.c_void_p()
+            L.call("pb_nnet_weights_device", one.h, C.byref(wp1))
+            L.call("pb_buffer_write_f32", ctx, wp1, w_start.ctypes.data, tw.value)
+            for t in range(2):
+                gx = torch.cat([a.view(2, B * 3072)[t] for a in xg]).contiguous()
+                ge = torch.cat([a.view(2, B * 10)[t] for a in eg]).contiguous()
+                torch.cuda.synchronize()
+                L.call("pb_nnet_batch_train", one.h, C.c_void_p(gx.data_ptr()),
+                       C.c_void_p(ge.data_ptr()), world * B)
+                L.call("pb_context_finish", ctx)
+            w_one = np.zeros(tw.value, dtype=np.float32)
+            L.call("pb_buffer_read_f32", ctx, wp1, w_one.ctypes.data, tw.value)
+            upd = float(np.abs(w_one.astype(np.float64) - w_start).max())
+            diff = float(np.abs(w_dp.astype(np.float64) - w_one).max())
+            dp_parity = {"ranks_identical": bool(identical),
+                         "max_rel_vs_single_gpu": diff / max(float(np.abs(w_one).max()), 1e-30),
+                         "max_diff_over_max_update": diff / max(upd, 1e-30),
+                         "how": "2 data-parallel steps vs the same 2 steps on one GPU over the global "
+                                "batch, from the same weights; max|w_dp - w_1| / max|w_1| (and relative "
+                                "to the largest weight change of the two steps)"}
+            del one
+        barrier()
+
+    # ---------------- the other BASELINE.json configurations ---------------------------------
+    other = None
+    if not args.no_other_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        other = {}
+
+        def attempt(name, fn):
+            try:
+                r = fn()
+                if rank == 0 and r is not None:
+                    other[name] = r
+            except Exception as ex:  # a side measurement must not take the headline down
+                if rank == 0:
+                    other[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
+        import bench_mlp
+        import bench_yolo
+        import bench_circle
+        cpu_flag = ["--cpu-baseline"] if (world == 1 and not args.no_cpu_baseline) else []
+        attempt("wide_mlp_train", lambda: bench_mlp.main(["--steps", "10", "--warmup", "3"] + cpu_flag,
+                                                         embedded=True))
+        barrier()
+        attempt("yolov1_forward", lambda: bench_yolo.main(["--steps", "3", "--warmup", "2"] + cpu_flag,
+                                                          embedded=True))
+        barrier()
+        if rank == 0:  # per-sample SGD does not shard: one GPU, replicas only
+            want_cpu = world == 1 and not args.no_cpu_baseline
+            attempt("circle_per_sample", lambda: bench_circle.circle(200000, local, want_cpu))
+            attempt("cifar_per_sample", lambda: bench_circle.cifar(2000, local, want_cpu))
+        barrier()
 
     # ---------------- per-kernel table + roofline (rank 0) ---------------------
     line = None
@@ -401,17 +510,19 @@ def run_ours(args):
         bf16_peak = peaks.get("bf16_tflops", 1590.0)
         top = rows[0]
 
-        mma_off = os.environ.get("PB_WGRAD_MMA") == "0" or os.environ.get("PB_DISABLE_UMMA") == "1"
+        umma_off = os.environ.get("PB_DISABLE_UMMA") == "1"
+        wgrad_umma = not umma_off and os.environ.get("PB_WGRAD_UMMA") != "0"
 
         def roofline_of(r):
             # which pipe the kernel group runs on: tcgen05 (fused conv forward, conv
-            # input-gradient), mma.sync (convolution weight gradients), FP32 FFMA (dense
-            # layers), or none (elementwise: HBM)
+            # input-gradient, conv weight gradient), FP32 FFMA (dense layers), or none
+            # (elementwise: HBM)
             k = r["kernel"]
-            tcgen05 = "tcgen05" in k or (k.startswith("convolution") and k.endswith(":input_delta"))
-            mma_sync = (not mma_off and k in ("convolution_layer_1:weight_update",
-                                              "convolution_layer_4:weight_update",
-                                              "convolution_layer_7:weight_update"))
+            wgrad = k in ("convolution_layer_1:weight_update", "convolution_layer_4:weight_update",
+                          "convolution_layer_7:weight_update")
+            tcgen05 = not umma_off and ("tcgen05" in k or (k.startswith("convolution") and
+                                        k.endswith(":input_delta")) or (wgrad and wgrad_umma))
+            mma_sync = wgrad and not wgrad_umma and not umma_off and os.environ.get("PB_WGRAD_MMA") != "0"
             tensor_peak = bf16_peak / 2 / 3
             if r["flop"] > 0 and not (tcgen05 or mma_sync):
                 out = {"bound": "fp32", "peak": tf.value, "unit": "TFLOP/s",
@@ -426,8 +537,12 @@ def run_ours(args):
                                        "algorithmic fp32 FLOPs",
                        "pipe": "mma.sync.m16n8k8 tf32 (warp-level; measured peak 278 TFLOP/s of tf32 "
                                "MMA work = 92.7 fp32-equivalent, tools/mma_sync_probe.cu)" if mma_sync
-                               else "tcgen05.mma kind::tf32, operands from shared memory (N <= 48: "
-                                    "bounded by operand fetch, DESIGN.md 3.2)"}
+                               else ("tcgen05.mma kind::tf32, gradient operand in tensor memory, image "
+                                     "operand K-major in shared memory (conv_wgrad_umma.cu); the time "
+                                     "includes the fixed-order partial reduce + SGD update kernel"
+                                     if wgrad else
+                                     "tcgen05.mma kind::tf32, operands from shared memory (N <= 48: "
+                                     "bounded by operand fetch, DESIGN.md 3.2)")}
             else:
                 out = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
@@ -457,6 +572,11 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
+            "timing": {"how": "median over blocks of `steps` steps; every block is bracketed by a "
+                              "barrier + synchronize on both sides, timed with CUDA events on the "
+                              "library stream, max over ranks",
+                       "blocks": len(blocks), "block_ms_min": min(blocks), "block_ms_max": max(blocks),
+                       "timed_seconds": sum(blocks) * 1e-3},
             "config": {"workload": "cifar_cnn_batch_train", "mode": "gradient_sum_minibatch",
                        "batch_per_gpu": B, "global_batch": B * world, "lr": 1e-4,
                        "loss": "cross_entropy",
@@ -480,6 +600,8 @@ def run_ours(args):
             "roofline_tensor": roof_tensor,
             "whole_step": whole,
             "cpu_baseline": cpu,
+            "dp_parity": dp_parity,
+            "other_configs": other,
             "step_kernels": [{"k": r["kernel"], "ms": round(r["ms"], 4)} for r in rows],
         }
         if args.table:
@@ -517,9 +639,14 @@ def _main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="samples per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-sample", type=int, default=256,
+    ap.add_argument("--ref-sample", type=int, default=1024,
                     help="samples per step of the CPU arm (bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="repeat the K-step block until this much time has been measured")
+    ap.add_argument("--max-blocks", type=int, default=400)
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the other BASELINE.json configurations (other_configs)")
     ap.add_argument("--table", default=None, help="write the per-kernel table (JSON) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -36,13 +36,16 @@ def mlp_model(pb, width, classes=10):
     return m
 
 
-def main():
+def main(argv=None, embedded=False):
+    """embedded=True (called from bench.py inside an initialised process group): returns the
+    line (rank 0) instead of printing it and leaves the process group alone."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--width", type=int, default=4096)
-    args = ap.parse_args()
+    ap.add_argument("--cpu-baseline", action="store_true", help="time the oracle port on a few samples")
+    args = ap.parse_args(argv)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -50,7 +53,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not embedded:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import plasticity_b200 as pb
@@ -122,6 +125,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop(t0, t1) if sampler else None
+    line = None
     if rank == 0:
         macs = Wd * Wd * 2 + Wd * 10
         flop_sample = 3 * 2.0 * macs
@@ -171,13 +175,38 @@ def main():
             cb["cores"] = recorded.get("host_cores")
             cb["note"] = "recorded by tools/cpu_baselines.py on the GPU box's host (not timed in this run)"
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        if args.cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(np, Wd)
+        if not embedded:
+            print(json.dumps(line))
     barrier()
     if comm is not None:
         L.call("pb_comm_destroy", comm)
-    if world > 1:
+    for p in (px, pe):
+        L.call("pb_buffer_free", ctx, p)
+    del net
+    if world > 1 and not embedded:
         dist.destroy_process_group()
-    return 0
+    return (line if rank == 0 else None) if embedded else 0
+
+
+def cpu_baseline(np, Wd, nb=4):
+    """The oracle's plain-C port of the reference arithmetic (fp64, OpenMP over examples) on
+    one gradient-sum step over nb samples: a bounded sample, the rate is per sample."""
+    from oracle import pyoracle as po
+    spec = (f"loss ce\nact {Wd} identity\ndense {Wd} {Wd}\nact {Wd} sigmoid\ndense {Wd} {Wd}\n"
+            f"act {Wd} sigmoid\ndense {Wd} 10\nact 10 identity\nsoftmax 10\n")
+    S = po.RestatedNet(spec)
+    rng = np.random.default_rng(0)
+    w = rng.normal(0, 1 / np.sqrt(Wd), S.total_w)
+    xs = rng.normal(0, 1, (nb, Wd))
+    es = np.zeros((nb, 10))
+    es[np.arange(nb), rng.integers(0, 10, nb)] = 1.0
+    t0 = time.perf_counter()
+    S.batch_train_mt(xs, es, w, 1e-4)
+    dt = time.perf_counter() - t0
+    return {"value": nb / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"one gradient-sum step over {nb} samples (OpenMP over examples, fp64)"}
 
 
 if __name__ == "__main__":

@@ -24,13 +24,16 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def main():
+def main(argv=None, embedded=False):
+    """embedded=True (called from bench.py inside an initialised process group): returns the
+    line (rank 0) instead of printing it and leaves the process group alone."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--global-batch", type=int, default=256)
     ap.add_argument("--width", type=int, default=448)
-    args = ap.parse_args()
+    ap.add_argument("--cpu-baseline", action="store_true", help="time the oracle port on one image")
+    args = ap.parse_args(argv)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -38,7 +41,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not embedded:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import plasticity_b200 as pb
@@ -89,6 +92,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop(t0, t1) if sampler else None
+    result = None
     if rank == 0:
         layers = net.model_.layers
         macs = 0
@@ -156,11 +160,33 @@ def main():
             cb["cores"] = recorded.get("host_cores")
             cb["note"] = "recorded by tools/cpu_baselines.py on the GPU box's host (not timed in this run)"
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        if args.cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(np)
+        result = line
+        if not embedded:
+            print(json.dumps(line))
     barrier()
-    if world > 1:
+    del yolo, net, x, out
+    torch.cuda.empty_cache()
+    if world > 1 and not embedded:
         dist.destroy_process_group()
-    return 0
+    return result if embedded else 0
+
+
+def cpu_baseline(np):
+    """The oracle's plain-C port of the reference arithmetic (fp64, one thread) on one image."""
+    from oracle import pyoracle as po
+    import plasticity_b200 as pb
+    from plasticity_b200 import yolov1
+    Y = po.RestatedNet(yolov1.YoloArchitecture().to_spec(pb.MeanSquared))
+    rng = np.random.default_rng(0)
+    wy = rng.standard_normal(Y.total_w) * 0.01
+    x = rng.uniform(0, 1, Y.n_in)
+    t0 = time.perf_counter()
+    Y.evaluate(x, wy)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "images/s", "cores": 1, "kind": "port",
+            "sample": "one 448x448x3 image forward (single thread, fp64)"}
 
 
 if __name__ == "__main__":
