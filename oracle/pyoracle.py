@@ -225,17 +225,20 @@ class RefNet(_NetBase):
     """The reference generator's emitted kernels, host-compiled (oracle/_ref)."""
 
     @staticmethod
-    def path(name: str) -> str:
-        return os.path.join(HERE, "_ref", f"libref_{name}.so")
+    def path(name: str, fp32: bool = False) -> str:
+        return os.path.join(HERE, "_ref", f"libref{'32' if fp32 else ''}_{name}.so")
 
     @classmethod
-    def available(cls, name: str) -> bool:
-        return os.path.exists(cls.path(name))
+    def available(cls, name: str, fp32: bool = False) -> bool:
+        return os.path.exists(cls.path(name, fp32))
 
-    def __init__(self, name: str):
-        if not self.available(name):
-            raise FileNotFoundError(self.path(name) + " (run `make -C oracle`)")
-        L = self.L = C.CDLL(self.path(name))
+    def __init__(self, name: str, fp32: bool = False):
+        """fp32=True: the same generated text evaluated in single precision (ref_shim.h
+        REF_FP32); only evaluate() is offered there."""
+        if not self.available(name, fp32):
+            raise FileNotFoundError(self.path(name, fp32) + " (run `make -C oracle`)")
+        L = self.L = C.CDLL(self.path(name, fp32))
+        self.fp32 = fp32
         self.name = name
         self.n_layers = L.ref_num_layers()
         self.loss = L.ref_loss()
@@ -288,8 +291,16 @@ class RefNet(_NetBase):
         return g
 
     def evaluate(self, x, weights):
-        lo = np.empty(self.total_o)
         w = weights if weights.size else np.zeros(1)
+        if self.fp32:
+            fp = C.POINTER(C.c_float)
+            x32 = np.ascontiguousarray(x, dtype=np.float32)
+            w32 = np.ascontiguousarray(w, dtype=np.float32)
+            lo32 = np.empty(self.total_o, dtype=np.float32)
+            self.L.ref_net_evaluate.argtypes = [fp, fp, fp]
+            self.L.ref_net_evaluate(x32.ctypes.data_as(fp), w32.ctypes.data_as(fp), lo32.ctypes.data_as(fp))
+            return lo32.astype(np.float64)
+        lo = np.empty(self.total_o)
         self.L.ref_net_evaluate(_p(x), _p(w), _p(lo))
         return lo
 

@@ -11,6 +11,10 @@
 #include <cstring>
 #include <vector>
 
+#ifdef REF_FP32  // fp32 variant of the checker (ref_shim.h): every buffer is float
+#define double float
+#endif
+
 extern "C" {
 int ref_parallel_threshold = 256;
 

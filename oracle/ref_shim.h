@@ -12,6 +12,16 @@
 
 using std::isinf;  // max_pool_layer.cc:80 emits a bare isinf()
 
+// REF_FP32: the SAME generated text evaluated in single precision (every `double` of the
+// emitted kernels becomes `float`; built with -fsingle-precision-constant so the printed
+// constants are float too).  Not what the reference runs - it exists to tell which max-pool
+// windows an fp32 evaluation in the reference's own summation order routes differently
+// from fp64 (tests/test_gpu_parity.py::test_pool_routing_unfiltered_inputs).  The system
+// headers above are already parsed; only the generated text and the driver see the macro.
+#ifdef REF_FP32
+#define double float
+#endif
+
 #define global
 #define kernel
 

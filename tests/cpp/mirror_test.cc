@@ -261,7 +261,107 @@ static void KernelQueue() {
   EXPECT_NEAR(w3_new[s.WeightNumber(0, 0)], 0.35891648, 1e-5);  // nnet_test.cc:260-273
 }
 
+// The cases of the reference's compute/cl_buffer_test.cc:48-227, restated for the mirror:
+// the cl::Buffer a caller assigns through `*buf.gpu_buffer() = cl_buffer` becomes a device
+// allocation the buffer adopts (operator= aliases the handle, cl_buffer.h:166-179).
+static void ClBufferCases() {
+  pb_context *ctx = nullptr;
+  PB_CHECK_OK(pb_context_create(0, &ctx));
+  auto fresh = [&] {
+    compute::ClBuffer b(5, ctx);
+    for (size_t i = 0; i < 5; ++i) b[i] = i * 2 + 1;
+    return b;
+  };
+  auto device_values = [&](double scale) {  // 5 doubles written straight to a device buffer
+    float *p = nullptr;
+    PB_CHECK_OK(pb_buffer_alloc(ctx, 5, &p));
+    double v[5];
+    for (size_t i = 0; i < 5; ++i) v[i] = i * scale;
+    PB_CHECK_OK(pb_buffer_write_f64(ctx, p, v, 5));
+    return compute::ClBuffer(ctx, p, 5);
+  };
+  {  // "CPU-only test" :48-63
+    compute::ClBuffer buf = fresh();
+    for (size_t i = 0; i < 5; ++i) EXPECT_TRUE(buf[i] == i * 2 + 1);
+  }
+  {  // "Moving to opencl and back doesnt kill values!" :78-84
+    compute::ClBuffer buf = fresh();
+    buf.MoveToGpu();
+    EXPECT_TRUE(buf.GetBufferLocation() == compute::ClBuffer::GPU && buf.size() == 5);
+    buf.MoveToCpu();
+    for (size_t i = 0; i < 5; ++i) EXPECT_TRUE(buf[i] == i * 2 + 1);
+  }
+  {  // "DeepClone in GPU mode doesn't ruin everything" :86-94
+    compute::ClBuffer buf = fresh();
+    buf.MoveToGpu();
+    auto buf2 = buf.DeepClone();
+    EXPECT_TRUE(buf2.gpu_buffer() != buf.gpu_buffer());  // a copy, not an alias
+    buf2.MoveToCpu();
+    buf.MoveToCpu();
+    for (size_t i = 0; i < 5; ++i) EXPECT_TRUE(buf[i] == buf2[i]);
+  }
+  {  // "Assigning via opencl doesn't kill values" :96-126
+    compute::ClBuffer buf = fresh();
+    buf.MoveToGpu();
+    buf = device_values(10);
+    buf.MoveToCpu();
+    for (size_t i = 0; i < 5; ++i) EXPECT_TRUE(buf[i] == i * 10);
+  }
+  {  // "opencl copy constructor" :128-184: 300 device-side copies, each moved both ways
+    compute::ClBuffer buf = fresh();
+    buf.MoveToGpu();
+    buf = device_values(10);
+    compute::ClBuffer buf2(buf);
+    for (size_t i = 0; i < 100; ++i) {
+      compute::ClBuffer buf3(buf2);
+      buf3.MoveToCpu();
+      buf3.MoveToGpu();
+      compute::ClBuffer buf4(buf3);
+      buf4.MoveToCpu();
+      buf4.MoveToGpu();
+      compute::ClBuffer buf5(buf4);
+      buf5.MoveToCpu();
+      buf5.MoveToGpu();
+    }
+    buf2.MoveToCpu();
+    for (size_t i = 0; i < 5; ++i) {
+      EXPECT_TRUE(buf2[i] == i * 10);
+      buf2[i] = i * 2 + 1;
+    }
+    buf2.MoveToGpu();
+    buf.MoveToCpu();  // the original is untouched by what happened to its copies
+    for (size_t i = 0; i < 5; ++i) EXPECT_TRUE(buf[i] == i * 10);
+  }
+  {  // "Assigning via cpu doesn't kill opencl values" :186-226
+    compute::ClBuffer buf = fresh();
+    buf.MoveToGpu();
+    buf.MoveToGpu();
+    buf = device_values(10);
+    buf.MoveToCpu();
+    buf.MoveToGpu();
+    buf.MoveToCpu();
+    for (size_t i = 0; i < 5; ++i) buf[i] = i * 2 + 1;
+    for (size_t i = 0; i < 100; ++i) {
+      buf.MoveToCpu();
+      buf.MoveToGpu();
+      buf.MoveToCpu();
+    }
+    for (size_t i = 0; i < 5; ++i) EXPECT_TRUE(buf[i] == i * 2 + 1);
+  }
+  {  // empty buffers and resize through the host, cl_buffer.cc:14-51
+    compute::ClBuffer buf(ctx);
+    buf.MoveToGpu();
+    EXPECT_TRUE(buf.size() == 0);
+    buf.resize(3, 7.0);
+    EXPECT_TRUE(buf.GetBufferLocation() == compute::ClBuffer::GPU && buf.size() == 3);
+    buf.MoveToCpu();
+    EXPECT_TRUE(buf[0] == 7.0 && buf[2] == 7.0);
+  }
+  PB_CHECK_OK(pb_context_destroy(ctx));
+}
+
 int main() {
+  ClBufferCases();
   KernelQueue();
   WorkgroupSizes();
   Yolo();

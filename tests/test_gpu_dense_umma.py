@@ -106,10 +106,11 @@ def test_wide_mlp_batch_train_step(ctx):
     util.load_product_weights(net, S, w0)
     w_ref = w0.copy()
     S.batch_train(xs.copy(), es.copy(), w_ref, lr)
+    # the deltas themselves (fp32, from the delta buffer) at the tolerance of record, then the
+    # step through BatchTrain (update fused into the weight-gradient kernels)
+    util.assert_close(util.device_deltas(net, S, xs, es), w_ref - w0, "wide MLP BatchTrain deltas")
     net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), B)
-    got = util.read_product_weights(net, S)
-    util.assert_close(got - w0, w_ref - w0, "wide MLP BatchTrain deltas", rtol=2e-4, atol_scale=2e-5)
-    util.assert_close(got, w_ref, "wide MLP BatchTrain weights")
+    util.assert_close(util.read_product_weights(net, S), w_ref, "wide MLP BatchTrain weights")
 
 
 def test_wide_classifier_head(ctx):
@@ -132,9 +133,9 @@ def test_wide_classifier_head(ctx):
     util.load_product_weights(net, S, w0)
     w_ref = w0.copy()
     S.batch_train(xs.copy(), es.copy(), w_ref, lr)
+    util.assert_close(util.device_deltas(net, S, xs, es), w_ref - w0, "wide head deltas")
     net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), B)
-    got = util.read_product_weights(net, S)
-    util.assert_close(got - w0, w_ref - w0, "wide head deltas", rtol=2e-4, atol_scale=2e-5)
+    util.assert_close(util.read_product_weights(net, S), w_ref, "wide head weights")
 
 
 @pytest.mark.parametrize("n_in,n_out,act,loss", [
@@ -168,10 +169,9 @@ def test_fused_head_shapes(ctx, n_in, n_out, act, loss):
         es[np.arange(B), rng.integers(0, n_out, B)] = 1.0
         w_before = w_ref.copy()
         S.batch_train(xs.copy(), es.copy(), w_ref, lr)
+        util.assert_close(util.device_deltas(net, S, xs, es), w_ref - w_before, f"head step {step} deltas")
         net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), B)
         got = util.read_product_weights(net, S)
-        util.assert_close(got - w_before, w_ref - w_before, f"head step {step} deltas",
-                          rtol=2e-4, atol_scale=2e-5)
         util.assert_close(got, w_ref, f"head step {step} weights")
         # keep the two trajectories from drifting apart through fp32 rounding
         util.load_product_weights(net, S, w_ref)

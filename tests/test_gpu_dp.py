@@ -1,9 +1,8 @@
 """Data-parallel gradient-sum training (the one exchange step of the path, SURVEY 8e;
 semantics nnet/nnet.h:624-669: W <- W - lr * sum over the GLOBAL batch) on real GPUs.
 
-* in-process rank groups (pb_comm_create_local): 2 and 3 ranks share the devices that are
-  there — on a single-GPU box all of them sit on cuda:0 — and run the same fused
-  exchange-and-update kernel over peer memory as the multi-process path;
+* in-process rank groups (pb_comm_create_local): 2 and 3 ranks share cuda:0 and run the same
+  fused exchange-and-update kernel over peer memory as the multi-process path;
 * with two or more GPUs, additionally the real thing: one process per GPU under
   torch.distributed.run (NCCL handshake, CUDA IPC).
 Every variant must leave bit-identical weights on all ranks, equal to the oracle's
@@ -54,7 +53,9 @@ def test_data_parallel_in_process_ranks(name, world, B):
     steps, lr = 3, 0.002
     spec, S, w0, xs, es, w_ref = make_case(name, steps, B, lr, zlib.crc32(name.encode()) + world)
     model, loss = util.architecture_from_spec(spec)
-    ndev = device_count()
+    # all in-process ranks on cuda:0 (the library keeps ONE current device per process, as in
+    # its one-process-per-GPU deployment); several devices are the multi-process test's job
+    ndev = 1
     ctxs = [pb.nnet.new_context(r % ndev) for r in range(world)]
     comms = pb.nnet.local_comms(ctxs)
     nets = []

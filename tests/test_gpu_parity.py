@@ -28,7 +28,7 @@ SPECS = sorted(os.path.basename(p)[:-5] for p in
 # savefmt contains a 2x2 / pad-0 convolution for which the reference's
 # input-gradient kernel indexes GRADIENT out of bounds (SURVEY 8c "parity
 # unpinned"); there the restatement (bounds-guarded) is the checker.
-REF_UNDEFINED = {"savefmt"}
+REF_UNDEFINED = {"savefmt", "nonsquare", "poolrem"}
 
 
 def checker(name):
@@ -162,8 +162,7 @@ def test_network_evaluate_train(ctx, name):
         _, ig_ref = R.train(xs[step].copy(), es[step].copy(), w_ref, lr, want_input_grads=True)
         ig.MoveToCpu()
         assert ig.size() == S.n_in
-        util.assert_close(ig.cpu, ig_ref, f"{name} input gradients step {step}", rtol=2e-4,
-                          atol_scale=5e-5)
+        util.assert_close(ig.cpu, ig_ref, f"{name} input gradients step {step}")
         if step in (0, 5):
             util.assert_close(util.read_product_weights(net, S), w_ref,
                               f"{name} weights after {step + 1} steps")
@@ -176,8 +175,7 @@ def test_network_evaluate_train(ctx, name):
     ig = net.MakeBuffer(0)
     net.Train(net.MakeBuffer(xs[0]), net.MakeBuffer(es[0]), ig, net.MakeBuffer(g0))
     ig.MoveToCpu()
-    util.assert_close(ig.cpu, ig_ref, f"{name} custom-gradient input gradients", rtol=2e-4,
-                      atol_scale=5e-5)
+    util.assert_close(ig.cpu, ig_ref, f"{name} custom-gradient input gradients")
     util.assert_close(util.read_product_weights(net, S), w_ref2, f"{name} custom-gradient weights")
 
 
@@ -486,3 +484,93 @@ def test_train_loop_cooperative_kernel(ctx, name, monkeypatch):
     R.train_loop(xs.copy(), es.copy(), w_ref, lr)
     net.TrainLoop(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), n)
     util.assert_close(util.read_product_weights(net, S), w_ref, f"{name} cooperative TrainLoop")
+
+
+def _pool_routing(layer_values, L_pool):
+    """Per window of a max-pool layer: index of the first maximum, whether the maximum is
+    unique, and the relative gap between the two largest values."""
+    D, H, W, oh, ow = L_pool.D, L_pool.H, L_pool.W, L_pool.oh, L_pool.ow
+    gh, gw = H // oh, W // ow
+    v = layer_values.reshape(D, H, W)[:, :oh * gh, :ow * gw].reshape(D, oh, gh, ow, gw)
+    win = v.transpose(0, 1, 3, 2, 4).reshape(-1, gh * gw)
+    srt = np.sort(win, axis=1)
+    gap = (srt[:, -1] - srt[:, -2]) / (np.abs(srt[:, -1]) + 1e-3)
+    return np.argmax(win, axis=1), gap
+
+
+def test_pool_routing_unfiltered_inputs(ctx):
+    """The fused tcgen05 convolution + activation + pool path on UNFILTERED inputs (no
+    pool-margin rejection, near-tie windows included).  Max-pool routing is a discontinuous
+    function of its inputs (max_pool_layer.cc:88-141 compares values): where the two largest
+    values of a window agree to rounding, fp32 and fp64 may pick different elements.
+      (i)   forward values of every layer the step materialises agree with the fp64 oracle at
+            1e-4 for every sample, near ties included;
+      (ii)  routing is bit-identical to the fp64 oracle AND to the fp32 evaluation of the same
+            reference-generated kernels wherever the top-2 gap exceeds 2e-5 (relative; four
+            times the measured 3xTF32 forward error of 5e-6);
+      (iii) the fraction of samples with ANY window routed differently from fp64 stays below
+            the 1/64 DESIGN.md states;
+      (iv)  the gradient-sum step over every sample routed like the oracle matches it at 1e-4."""
+    name = "cifar"
+    if not (po.RefNet.available(name) and po.RefNet.available(name, fp32=True)):
+        pytest.fail("oracle/_ref (fp64 and fp32 builds of the reference-generated kernels) missing")
+    spec = po.spec_text(name)
+    S = po.RestatedNet(spec)
+    R, R32 = po.RefNet(name), po.RefNet(name, fp32=True)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(20261020)
+    w0 = util.xavier_like(S, rng)
+    B, lr = 256, 0.002
+    xs = util.f32(rng.normal(0, 1, (B, S.n_in)))
+    es = util.f32(rng.uniform(0, 1, (B, S.n_out)))
+    net = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=B)
+    net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+    util.load_product_weights(net, S, w0)
+    dx, de = Dev(ctx, xs), Dev(ctx, es)
+    net._sync_to_device()
+    L.call("pb_nnet_batch_gradients", net.h, dx.p, de.p, B)
+    pools = [l for l in range(S.n_layers) if S.layers[l].kind == po.KINDS["pool"]]
+    assert len(pools) == 3
+
+    def device_layer(l):
+        p = C.c_void_p()
+        L.call("pb_nnet_layer_output", net.h, l, C.byref(p))
+        out = np.empty(B * S.no[l])
+        L.call("pb_buffer_read_f64", ctx, p, out.ctypes.data, out.size)
+        return out.reshape(B, S.no[l])
+
+    dev_conv = {l: device_layer(l - 2) for l in pools}     # convolution output (pre-activation)
+    dev_pool = {l: device_layer(l) for l in pools}
+    flipped = np.zeros(B, dtype=bool)
+    flipped32 = np.zeros(B, dtype=bool)
+    clear_windows = 0
+    for b in range(B):
+        lo = R.evaluate(xs[b].copy(), w0.copy())
+        lo32 = R32.evaluate(xs[b].copy(), w0.copy())
+        for l in pools:
+            conv_ref = R.layer_output(lo, l - 2)
+            util.assert_close(dev_conv[l][b], conv_ref, f"sample {b} convolution {l - 2} output")
+            util.assert_close(dev_pool[l][b], R.layer_output(lo, l), f"sample {b} pool {l} output")
+            # LeakyReLU is strictly increasing: the pool's winner is the convolution's winner
+            a_ref, gap = _pool_routing(R.layer_output(lo, l - 1), S.layers[l])
+            a_32, _ = _pool_routing(R32.layer_output(lo32, l - 1), S.layers[l])
+            a_dev, _ = _pool_routing(dev_conv[l][b], S.layers[l])
+            clear = gap > 2e-5
+            clear_windows += int(clear.sum())
+            assert np.array_equal(a_dev[clear], a_ref[clear]), f"sample {b} pool {l}: clear window routed differently"
+            assert np.array_equal(a_32[clear], a_ref[clear]), f"sample {b} pool {l}: fp32 oracle differs on a clear window"
+            flipped[b] |= bool((a_dev != a_ref).any())
+            flipped32[b] |= bool((a_32 != a_ref).any())
+    rate = flipped.mean()
+    print(f"pool routing: {int(flipped.sum())}/{B} samples with a window routed differently from fp64 "
+          f"(fp32 evaluation of the reference kernels: {int(flipped32.sum())}/{B}); {clear_windows} clear windows identical")
+    assert rate <= 1.0 / 64 + 1e-12, f"mis-route rate {rate:.4f} above 1/64"
+    keep = np.flatnonzero(~flipped)
+    w_ref = w0.copy()
+    R.batch_train(np.ascontiguousarray(xs[keep]), np.ascontiguousarray(es[keep]), w_ref, lr)
+    net2 = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=len(keep))
+    net2.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+    util.load_product_weights(net2, S, w0)
+    net2.BatchTrain(net2.MakeBuffer(xs[keep].reshape(-1)), net2.MakeBuffer(es[keep].reshape(-1)), len(keep))
+    util.assert_close(util.read_product_weights(net2, S), w_ref,
+                      f"gradient-sum step over the {len(keep)} unfiltered samples routed like the oracle")

@@ -124,3 +124,29 @@ def draw_with_pool_margin(onet, rng, n, weights, margin=2e-5, scale=1.0):
         if pool_margin(onet, x, weights) >= margin:
             out.append(x)
     return np.stack(out)
+
+
+def device_deltas(pnet, onet, xs, es):
+    """-lr * sum_b grad_b as the device forms it (pb_nnet_batch_gradients: the weight-gradient
+    kernels in WEIGHT_DELTAS mode), read from the flat delta buffer in the oracle's layout -
+    the fp32 deltas themselves, not a difference of rounded weights."""
+    import ctypes as C
+    from plasticity_b200 import _lib as L
+    B = xs.shape[0]
+    bx, be = pnet.MakeBuffer(xs.reshape(-1)), pnet.MakeBuffer(es.reshape(-1))
+    bx.MoveToGpu()
+    be.MoveToGpu()
+    pnet._sync_to_device()
+    L.call("pb_nnet_batch_gradients", pnet.h, bx.gpu_buffer(), be.gpu_buffer(), B)
+    dp = C.c_void_p()
+    L.call("pb_nnet_deltas_device", pnet.h, C.byref(dp))
+    n_flat = sum((n + 3) & ~3 for n in onet.nw)
+    flat = np.zeros(n_flat, dtype=np.float32)
+    L.call("pb_buffer_read_f32", pnet.ctx, dp, flat.ctypes.data_as(C.c_void_p), n_flat)
+    out = np.zeros(onet.total_w)
+    off = 0
+    for l in range(onet.n_layers):
+        n = onet.nw[l]
+        out[onet.w_off[l]:onet.w_off[l + 1]] = flat[off:off + n]
+        off += (n + 3) & ~3
+    return out
