@@ -138,12 +138,19 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, const float *bias_
   }
 }
 
-// ACT >= 0: fused epilogue — additionally writes Out2 = 2x2 max-pool of
+// ACT >= 0, forward: fused epilogue - additionally writes Out2 = 2x2 max-pool of
 // act(conv output) (MaxPoolLayer forward of ActivationLayer forward).
+// ACT >= 0, input gradient (BWD): fused PRODUCER - `In` is the gradient of the 2x2 max-pool's
+// OUTPUT (H/2 x W/2 per channel) and Aux the stored convolution output of the layer whose
+// gradient this is; the producers form dE/d(conv output) = act'(O) * (act(O) is a maximum of
+// its window ? Gp : 0) on the fly (max_pool_layer.cc:88-141 + activation_layer.cc:13-22,
+// value for value what act_pool_bwd_kernel computes), feed it to the MMAs and also write it
+// to Out2 for the weight-gradient kernel: no stand-alone pool / activation backward pass.
 template <class C, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
-                 float *__restrict__ Out, float *__restrict__ Out2, int batch, int early_w) {
+                 float *__restrict__ Out, float *__restrict__ Out2, int batch, int early_w,
+                 const float *__restrict__ Aux) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float4 *a_s = reinterpret_cast<float4 *>(smem_raw);         // [2][A_STAGE]
   float4 *b_s = a_s + 2 * C::A_STAGE;                         // [B_UNITS]
@@ -230,6 +237,86 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
     constexpr int TOTAL = C::CH * C::SR * C::W;
     constexpr int ITERS = (TOTAL + kProducers - 1) / kProducers;
     int it = 0;
+    if constexpr (C::BWD && ACT >= 0) {
+      // one thread = one 2x2 pool window x one 4-channel chunk: 16 gradient values from
+      // 8 float2 loads of the convolution output and 4 pooled gradients
+      constexpr int ACTV = ACT >= 0 ? ACT : 0;
+      constexpr int WW = C::W / 2, WR = C::SR / 2;       // windows per row, window rows per item
+      constexpr int WTOTAL = C::CH * WR * WW;
+      constexpr int WITERS = (WTOTAL + kProducers - 1) / kProducers;
+      static_assert(C::SR % 2 == 0 && C::PAD % 2 == 0 && C::RI % 2 == 0, "window-aligned rows");
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        const int b = item / C::IPS, rb = item - b * C::IPS;
+        const int y0 = rb * C::RI - C::PAD;               // even: shared-memory rows pair up as windows
+        float4 *hi = a_s + s * C::A_STAGE;
+        float4 *lo = hi + C::CH * C::PL;
+        const float *o_src = Aux + (int64_t)b * C::IC * C::H * C::W;
+        const float *g_src = In + (int64_t)b * C::IC * (C::H / 2) * (C::W / 2);
+        float *g_dst = Out2 + (int64_t)b * C::IC * C::H * C::W;
+        float2 o0[WITERS][4], o1[WITERS][4];
+        float gp[WITERS][4];
+#pragma unroll
+        for (int k = 0; k < WITERS; ++k) {
+          const int e = ptid + k * kProducers;
+          const int xw = e % WW, t = e / WW;
+          const int wr = t % WR, c = t / WR;
+          const int y = y0 + 2 * wr;
+          const bool ok = e < WTOTAL && y >= 0 && y < C::H;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ic = 4 * c + i;
+            const bool live = ok && ic < C::IC;
+            const float *po = o_src + ((int64_t)ic * C::H + y) * C::W + 2 * xw;
+            o0[k][i] = live ? __ldg(reinterpret_cast<const float2 *>(po)) : make_float2(0.f, 0.f);
+            o1[k][i] = live ? __ldg(reinterpret_cast<const float2 *>(po + C::W)) : make_float2(0.f, 0.f);
+            gp[k][i] = live ? __ldg(g_src + ((int64_t)ic * (C::H / 2) + (y >> 1)) * (C::W / 2) + xw) : 0.0f;
+          }
+        }
+        mbar_wait(&a_empty[s], ph ^ 1);
+#pragma unroll
+        for (int k = 0; k < WITERS; ++k) {
+          const int e = ptid + k * kProducers;
+          if (e < WTOTAL) {
+            const int xw = e % WW, t = e / WW;
+            const int wr = t % WR, c = t / WR;
+            const int y = y0 + 2 * wr;
+            const bool inside = y >= 0 && y < C::H;
+            // rows of this item's own band (not the halo shared with its neighbours)
+            const bool own = inside && 2 * wr >= C::PAD && 2 * wr < C::PAD + C::RI;
+            float d[4][4];  // [pixel 00 01 10 11][channel]
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float a00 = act_fwd<ACTV>(o0[k][i].x), a01 = act_fwd<ACTV>(o0[k][i].y);
+              const float a10 = act_fwd<ACTV>(o1[k][i].x), a11 = act_fwd<ACTV>(o1[k][i].y);
+              const float m = fmaxf(fmaxf(a00, a01), fmaxf(a10, a11));
+              const float g = gp[k][i];
+              d[0][i] = act_bwd<ACTV>(o0[k][i].x, a00 < m ? 0.0f : g);
+              d[1][i] = act_bwd<ACTV>(o0[k][i].y, a01 < m ? 0.0f : g);
+              d[2][i] = act_bwd<ACTV>(o1[k][i].x, a10 < m ? 0.0f : g);
+              d[3][i] = act_bwd<ACTV>(o1[k][i].y, a11 < m ? 0.0f : g);
+              const int ic = 4 * c + i;
+              if (own && ic < C::IC) {
+                float *pg = g_dst + ((int64_t)ic * C::H + y) * C::W + 2 * xw;
+                *reinterpret_cast<float2 *>(pg) = make_float2(d[0][i], d[1][i]);
+                *reinterpret_cast<float2 *>(pg + C::W) = make_float2(d[2][i], d[3][i]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float v0 = inside ? d[q][0] : 0.0f, v1 = inside ? d[q][1] : 0.0f,
+                          v2 = inside ? d[q][2] : 0.0f, v3 = inside ? d[q][3] : 0.0f;
+              const float h0 = tf32_hi(v0), h1 = tf32_hi(v1), h2 = tf32_hi(v2), h3 = tf32_hi(v3);
+              const int pix = c * C::PL + (2 * wr + (q >> 1)) * C::P + 2 * xw + (q & 1) + C::PAD;
+              hi[pix] = make_float4(h0, h1, h2, h3);
+              lo[pix] = make_float4(v0 - h0, v1 - h1, v2 - h2, v3 - h3);
+            }
+          }
+        }
+        fence_async_proxy();
+        mbar_arrive(&a_full[s]);
+      }
+    } else
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       const int b = item / C::IPS, rb = item - b * C::IPS;
@@ -365,11 +452,14 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
         const uint32_t taddr =
             tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * C::TMEM_STAGE + tile * C::N1);
         float *dst = Out + (((int64_t)b * C::OC) * C::H + r) * C::W + tile * 8 + xin;
-        float *dst2 = ACT >= 0 ? Out2 + (((int64_t)b * C::OC) * (C::H / 2) + (r >> 1)) * (C::W / 2) +
-                                     ((tile * 8 + xin) >> 1)
-                               : nullptr;
-        if (half == 0) epilogue_tile<C, ACT, 0>(taddr, bias_s, dst, dst2, row_ok, writer);
-        else epilogue_tile<C, ACT, 1>(taddr, bias_s, dst, dst2, row_ok, writer);
+        // the fused activation + pool epilogue belongs to the FORWARD kernel only (in the
+        // input-gradient kernel ACT selects the fused producer and Out2 is its output)
+        constexpr int EACT = C::BWD ? -1 : ACT;
+        float *dst2 = EACT >= 0 ? Out2 + (((int64_t)b * C::OC) * (C::H / 2) + (r >> 1)) * (C::W / 2) +
+                                      ((tile * 8 + xin) >> 1)
+                                : nullptr;
+        if (half == 0) epilogue_tile<C, EACT, 0>(taddr, bias_s, dst, dst2, row_ok, writer);
+        else epilogue_tile<C, EACT, 1>(taddr, bias_s, dst, dst2, row_ok, writer);
       }
       tc_fence_before();
       mbar_arrive(&d_empty[s]);
@@ -388,7 +478,7 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
 
 template <class C, int ACT = -1>
 int launch_umma(pb_context *ctx, const float *In, const float *Wt, float *Out, int64_t batch,
-                float *Out2 = nullptr) {
+                float *Out2 = nullptr, const float *Aux = nullptr) {
   auto kern = conv_umma_kernel<C, ACT>;
   static bool configured = false;
   if (!configured) {
@@ -399,7 +489,7 @@ int launch_umma(pb_context *ctx, const float *In, const float *Wt, float *Out, i
   const int grid = (int)std::min<int64_t>(n_items, ctx->num_sms);
   const int early_w = ctx->chain == 2;
   PB_CUDA(launch_chained(ctx, kern, dim3(grid), dim3(kThreads), C::SMEM, In, Wt, Out, Out2,
-                         (int)batch, early_w));
+                         (int)batch, early_w, Aux));
   PB_LAUNCHED(ctx);
   return 0;
 }
@@ -464,6 +554,38 @@ int conv_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, const float *
   if (w == 32 && d == 3 && f == 16) return launch_umma<UCfg<16, 3, 32, 32, 5, true, true>>(ctx, G, W, dI, batch);
   if (w == 16 && d == 16 && f == 20) return launch_umma<UCfg<20, 16, 16, 16, 5, true>>(ctx, G, W, dI, batch);
   if (w == 8 && d == 20 && f == 20) return launch_umma<UCfg<20, 20, 8, 8, 5, true>>(ctx, G, W, dI, batch);
+  return -1;
+}
+
+template <class C>
+static int launch_fused_bwd(pb_context *ctx, int act, const float *Gp, const float *W, float *dI,
+                            float *G_out, const float *O_conv, int64_t batch) {
+  switch (act) {
+    case PB_IDENTITY: return launch_umma<C, PB_IDENTITY>(ctx, Gp, W, dI, batch, G_out, O_conv);
+    case PB_RELU: return launch_umma<C, PB_RELU>(ctx, Gp, W, dI, batch, G_out, O_conv);
+    case PB_LEAKY_RELU: return launch_umma<C, PB_LEAKY_RELU>(ctx, Gp, W, dI, batch, G_out, O_conv);
+    case PB_SIGMOID: return launch_umma<C, PB_SIGMOID>(ctx, Gp, W, dI, batch, G_out, O_conv);
+  }
+  return -1;
+}
+
+// Input gradient of a convolution -> activation -> exact 2x2 max-pool block in ONE kernel:
+// Gp = dE/d(pool output); writes dI = dE/d(convolution input) and G_out = dE/d(convolution
+// output) (for the weight-gradient kernel that follows).  -1 outside the envelope.
+int conv_act_pool_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, int act,
+                                   const pb_layer_desc *pool, const float *W, const float *O_conv,
+                                   const float *Gp, float *G_out, float *dI, int64_t batch) {
+  if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
+  if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
+  if (l->width != l->height) return -1;
+  const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
+  if (pool->width != w || pool->height != w || pool->depth != f || pool->out_width * 2 != w ||
+      pool->out_height * 2 != w)
+    return -1;
+  if ((((uintptr_t)O_conv) | ((uintptr_t)G_out)) & 7) return -1;
+  if (w == 32 && d == 3 && f == 16) return launch_fused_bwd<UCfg<16, 3, 32, 32, 5, true, true>>(ctx, act, Gp, W, dI, G_out, O_conv, batch);
+  if (w == 16 && d == 16 && f == 20) return launch_fused_bwd<UCfg<20, 16, 16, 16, 5, true>>(ctx, act, Gp, W, dI, G_out, O_conv, batch);
+  if (w == 8 && d == 20 && f == 20) return launch_fused_bwd<UCfg<20, 20, 8, 8, 5, true>>(ctx, act, Gp, W, dI, G_out, O_conv, batch);
   return -1;
 }
 

@@ -93,6 +93,12 @@ int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *conv, int 
                                 const pb_layer_desc *pool, const float *I, const float *W,
                                 float *O_conv, float *O_pool, int64_t batch);
 
+// the backward of such a block: pool + activation backward formed inside the producers of the
+// input-gradient kernel; also writes G_out = dE/d(convolution output) for the weight gradient.
+int conv_act_pool_input_delta_umma(pb_context *ctx, const pb_layer_desc *conv, int act,
+                                   const pb_layer_desc *pool, const float *W, const float *O_conv,
+                                   const float *Gp, float *G_out, float *dI, int64_t batch);
+
 // conv_gemm_umma.cu: general implicit-GEMM tensor-core convolution (forward) for large
 // batched shapes, any filter / stride / padding; O2 != nullptr additionally receives
 // act(O), the output of a following ActivationLayer.  -1 outside the envelope.

@@ -29,6 +29,7 @@ struct pb_nnet {
   float *weights = nullptr, *deltas = nullptr;
   std::vector<float *> outputs;
   float *grad_a = nullptr, *grad_b = nullptr;
+  float *grad_c = nullptr;  // dE/d(convolution output) of a fused block (allocated on first use)
   float *lr = nullptr;
   float *err = nullptr;  // n_out loss components
   // strict per-sample SGD loop (pb_nnet_train_loop)
@@ -192,6 +193,39 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
   for (int l = top; l >= 0; --l) {
     const pb_layer_desc *L = &net->layers[l];
     if (l == 0 && net->alias_input && n > 1) break;  // dE/dInput == g, unobserved here
+    if (l >= 2 && net->block[l - 2] && L->kind == PB_MAX_POOL && fused_fwd[l - 2]) {
+      // The whole block backward in two kernels: the convolution's input-gradient kernel forms
+      // dE/d(conv output) from the pooled gradient and the stored convolution output inside
+      // its producers (and writes it out once, for the weight gradient that follows).
+      const int cl = l - 2;
+      if (!net->grad_c) {
+        if (cudaMalloc((void **)&net->grad_c, sizeof(float) * (size_t)(net->max_io * net->max_batch)) !=
+            cudaSuccess) {
+          cudaGetLastError();
+          net->grad_c = nullptr;
+        }
+      }
+      float *Wc = net->weights + net->w_off[cl];
+      const int frc = net->grad_c ? conv_act_pool_input_delta_umma(
+                                        net->ctx, &net->layers[cl], net->layers[l - 1].activation, L,
+                                        Wc, net->outputs[cl], g, net->grad_c, ng, batch)
+                                  : -1;
+      if (frc > 0) return 1;
+      if (frc == 0) {
+        mark(net, layer_tag(net, cl) + ":input_delta+activation+pool backward (tcgen05)");
+        const float *in = layer_in[cl] ? layer_in[cl] : net->outputs[cl - 1];
+        const int m = in_place ? PB_NEW_WEIGHTS : first_chunk ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
+        float *out = in_place ? Wc : net->deltas + net->w_off[cl];
+        if (pb_layer_weight_update(net->ctx, &net->layers[cl], in, Wc, net->grad_c, out, net->lr, m,
+                                   batch))
+          return 1;
+        mark(net, layer_tag(net, cl) + ":weight_update");
+        if (!in_place && fire_delta_hook(net, cl, last_chunk)) return 1;
+        float *t = g; g = ng; ng = t;
+        l = cl;  // pool, activation and convolution are done
+        continue;
+      }
+    }
     if (l >= 2 && net->block[l - 2] && L->kind == PB_MAX_POOL) {
       // pool + activation backward in one pass over the convolution output
       const int rc = act_pool_input_delta(net->ctx, net->layers[l - 1].activation, L,
@@ -504,6 +538,7 @@ int pb_nnet_destroy(pb_nnet *net) {
     if (sg.exec) cudaGraphExecDestroy(sg.exec);
   cudaFree(net->weights); cudaFree(net->deltas);
   cudaFree(net->grad_a); cudaFree(net->grad_b);
+  if (net->grad_c) cudaFree(net->grad_c);
   cudaFree(net->lr); cudaFree(net->err);
   cudaFree(net->stage_in); cudaFree(net->stage_exp); cudaFree(net->cursor);
   for (float *p : net->outputs) cudaFree(p);
