@@ -507,6 +507,10 @@ bool umma_enabled() {
 // Returns -1 when the shape is outside the tensor-core kernels' envelope.
 int conv_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
                        float *O, int64_t batch) {
+  {
+    const int rc = conv_evaluate_wt(ctx, l, I, W, O, batch);
+    if (rc >= 0) return rc;
+  }
   if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
   if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
   if (l->width != l->height) return -1;
@@ -532,6 +536,10 @@ static int launch_fused(pb_context *ctx, int act, const float *I, const float *W
 int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, int act,
                                 const pb_layer_desc *pool, const float *I, const float *W,
                                 float *O, float *O2, int64_t batch) {
+  {
+    const int rc = conv_act_pool_evaluate_wt(ctx, l, act, pool, I, W, O, O2, batch);
+    if (rc >= 0) return rc;
+  }
   if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
   if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
   if (l->width != l->height) return -1;
@@ -547,6 +555,10 @@ int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, int act
 
 int conv_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, const float *W, const float *G,
                           float *dI, int64_t batch) {
+  {
+    const int rc = conv_input_delta_wt(ctx, l, W, G, dI, batch);
+    if (rc >= 0) return rc;
+  }
   if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
   if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
   if (l->width != l->height) return -1;
@@ -575,6 +587,10 @@ static int launch_fused_bwd(pb_context *ctx, int act, const float *Gp, const flo
 int conv_act_pool_input_delta_umma(pb_context *ctx, const pb_layer_desc *l, int act,
                                    const pb_layer_desc *pool, const float *W, const float *O_conv,
                                    const float *Gp, float *G_out, float *dI, int64_t batch) {
+  {
+    const int rc = conv_act_pool_input_delta_wt(ctx, l, act, pool, W, O_conv, Gp, G_out, dI, batch);
+    if (rc >= 0) return rc;
+  }
   if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
   if (l->filter_width != 5 || l->filter_height != 5 || l->padding != 2) return -1;
   if (l->width != l->height) return -1;
