@@ -685,8 +685,7 @@ int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const floa
   g.batch = (int)batch;
   if (g.F > 32) return -1;
   if (fw == 5 && fh == 5) {
-    static const bool use_ws = !(getenv("PB_WGRAD_WS") && getenv("PB_WGRAD_WS")[0] == '0');
-    if (use_ws && g.W == g.ow && g.H == g.oh && g.ow == g.oh) {
+    if (g.W == g.ow && g.H == g.oh && g.ow == g.oh) {
       int rc = -1;
       if (g.ow == 32) rc = launch_wgrad_ws<5, 5, 4, 32, 768>(ctx, I, Wt, G, out, lr, mode, g);
       else if (g.ow == 16) rc = launch_wgrad_ws<5, 5, 4, 16, 896>(ctx, I, Wt, G, out, lr, mode, g);
@@ -697,12 +696,6 @@ int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const floa
         else if (g.ow == 8) rc = launch_wgrad_ws<5, 5, 4, 8, 1024>(ctx, I, Wt, G, out, lr, mode, g);
       }
       if (rc >= 0) return rc;
-    }
-    static const int maxt = getenv("PB_WGRAD_T") ? atoi(getenv("PB_WGRAD_T")) : 1024;
-    if (maxt == 512) {
-      if (g.ow == 32) return launch_wgrad<5, 5, 4, 32, 512>(ctx, I, Wt, G, out, lr, mode, g);
-      if (g.ow == 16) return launch_wgrad<5, 5, 4, 16, 512>(ctx, I, Wt, G, out, lr, mode, g);
-      if (g.ow == 8) return launch_wgrad<5, 5, 4, 8, 512>(ctx, I, Wt, G, out, lr, mode, g);
     }
     if (g.ow == 32) return launch_wgrad<5, 5, 4, 32>(ctx, I, Wt, G, out, lr, mode, g);
     if (g.ow == 16) return launch_wgrad<5, 5, 4, 16>(ctx, I, Wt, G, out, lr, mode, g);

@@ -486,8 +486,7 @@ int conv_weight_update_umma(pb_context *ctx, const pb_layer_desc *l, const float
   // The RGB layer (3 -> 16 channels, N = 30) is bound by producing the gradient operand
   // (80 rows x 40 columns x hi/lo per image row through shared memory and tcgen05.st): 77 us
   // against 58 us of the mma.sync kernel of conv_wgrad_mma.cu, which therefore keeps it.
-  static const bool rgb = getenv("PB_WGRAD_UMMA_RGB") != nullptr;
-  if (rgb && w == 32 && d == 3 && f == 16) return launch<GCfg<3, 16, 32, 16, true, 3, 6>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
+  // (kept instantiable: GCfg<3, 16, 32, 16, true, 3, 6> is that configuration)
   return -1;
 }
 

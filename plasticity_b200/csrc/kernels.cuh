@@ -125,13 +125,6 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
                      const int64_t *w_off, int64_t total_w, int loss, float *weights,
                      const float *lr, const float *d_ins, const float *d_expected,
                      int64_t n_samples);
-// train_coop.cu: the same loop for any layer list as one cooperative persistent kernel
-// (opt-in, PB_TRAIN_COOP=1); -1 when not selected / outside its envelope
-int train_loop_coop(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
-                    const int64_t *w_off, int loss, float *weights, const float *lr,
-                    float *const *outputs, float *grad_a, float *grad_b, const float *d_ins,
-                    const float *d_expected, int64_t n_samples);
-
 // records.cu: pb_records_decode on an explicit stream.
 int records_decode_on(pb_context *ctx, cudaStream_t stream, const uint8_t *d_records,
                       float *d_inputs, float *d_expected, int64_t n_records, int64_t sample_size,

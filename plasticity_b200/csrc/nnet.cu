@@ -676,14 +676,6 @@ int pb_nnet_train_loop(pb_nnet *net, const float *d_ins, const float *d_expected
                                         net->lr, d_ins, d_expected, n_samples);
     if (rc >= 0) return rc;
   }
-  {
-    // any layer list: one cooperative persistent kernel, grid barriers instead of launches
-    const int rc = pb::train_loop_coop(ctx, net->layers.data(), (int)net->layers.size(),
-                                       net->w_off.data(), net->loss, net->weights, net->lr,
-                                       net->outputs.data(), net->grad_a, net->grad_b, d_ins,
-                                       d_expected, n_samples);
-    if (rc >= 0) return rc;
-  }
   if (!net->train_exec) {
     // Capture ONE Train() (fetch sample -> forward -> error gradient ->
     // reverse loop with in-place SGD -> advance cursor) into a CUDA graph.

@@ -136,25 +136,51 @@ train_small_kernel(const SmallNet net, float *__restrict__ W_global, const float
 }
 
 // ---- one-warp variant: every layer at most 32 values wide --------------------------------
-// Lane j owns value j of every layer, so a step needs no CTA barrier at all (__syncwarp
-// only).  Dense weights live in shared memory TRANSPOSED with pitch 33 —
-// wT[i * 33 + o] = W[o][i], row nin = the biases — so that both the forward product (fixed
-// input i, lanes = outputs) and the input gradient (fixed output o, lanes = inputs) read
-// conflict-free, and the activations of a layer are read as broadcasts.  The gradient vector
-// lives in one register per lane.  Same arithmetic and accumulation order as the kernel
-// above (ascending-index FMA chains; the softmax denominator is summed in ascending order
-// from the per-lane exponentials).
+// Lane j owns value j of every layer.  The value a layer has just produced stays in a
+// REGISTER and is handed to the next layer with shuffles (a dense product is one
+// LDS + SHFL + FMA per input); the per-layer activations are also stored to shared memory,
+// but only their own lane ever reads them back (the backward pass), so the forward pass has
+// no synchronisation at all.  Dense weights live in shared memory TRANSPOSED with pitch 33 —
+// wT[i * 33 + o] = W[o][i], row nin = the biases — so that the forward product and the
+// update (lane = output o, own column) and the input gradient (lane = input i, own row) all
+// read conflict-free; the only cross-lane hand-over through memory is update -> next
+// sample's input gradient, one __syncwarp per dense layer and sample.  Same arithmetic and
+// accumulation order as the kernel above (ascending-index FMA chains; the softmax denominator
+// is summed in ascending order).
 constexpr int kWarpPitch = 33;
+constexpr unsigned kFull = 0xffffffffu;
 
+// acc = bias + sum_i w[i][lane] * x_i (ascending i), x_i = value i of `cur`; eight inputs at a
+// time: all loads and shuffles of a batch are issued before its FMA chain, so a single
+// in-order warp pays the shared-memory / shuffle latency once per eight inputs, not per input
+__device__ __forceinline__ float warp_dense_fwd(const float *w, int nin, float cur, float acc, bool live) {
+  for (int i0 = 0; i0 < nin; i0 += 8) {
+    float wv[8], xv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = min(i0 + k, nin - 1);
+      wv[k] = w[i * kWarpPitch];
+      xv[k] = __shfl_sync(kFull, cur, i);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (live && i0 + k < nin) acc = fmaf(wv[k], xv[k], acc);
+  }
+  return acc;
+}
+
+// NL > 0: the layer loops are unrolled for exactly NL layers (every per-layer parameter is a
+// constant-bank operand instead of a dependent indexed load); NL == 0: any layer count.
+template <int NL>
 __global__ void __launch_bounds__(32, 1)
 train_warp_kernel(const SmallNet net, float *__restrict__ W_global, const float *__restrict__ lr_p,
                   const float *__restrict__ ins, const float *__restrict__ expected,
                   long long n_samples) {
   extern __shared__ float sm[];
+  const int n_layers = NL ? NL : net.n_layers;
   float *acts = sm + net.wt_total;                 // [n_layers + 1][32]: acts[0] = the sample
-  float *gs = acts + (net.n_layers + 1) * 32;      // [32] broadcast buffer
   const int lane = threadIdx.x;
-  for (int l = 0; l < net.n_layers; ++l) {
+  for (int l = 0; l < n_layers; ++l) {
     if (net.kind[l] != PB_DENSE) continue;
     const int ld = net.nin[l] + 1;
     for (int idx = lane; idx < net.nout[l] * ld; idx += 32) {
@@ -171,82 +197,94 @@ train_warp_kernel(const SmallNet net, float *__restrict__ W_global, const float 
   __syncwarp();
 
   for (long long s = 0; s < n_samples; ++s) {
-    if (lane < net.n_in) acts[lane] = x_next;
+    float cur = x_next;                             // value `lane` of the current layer's input
     const float e_cur = e_next;
+    acts[lane] = cur;
     if (s + 1 < n_samples) {
       if (lane < net.n_in) x_next = ins[(s + 1) * net.n_in + lane];
       if (lane < net.n_out) e_next = expected[(s + 1) * net.n_out + lane];
     }
-    __syncwarp();
     // ---- forward ---------------------------------------------------------------
-    for (int l = 0; l < net.n_layers; ++l) {
-      const float *I = acts + l * 32;
-      float *O = acts + (l + 1) * 32;
+#pragma unroll
+    for (int l = 0; l < n_layers; ++l) {
       const int nin = net.nin[l], nout = net.nout[l];
+      float out = 0.0f;
       if (net.kind[l] == PB_ACTIVATION) {
-        if (lane < nout) O[lane] = act_fwd_rt(net.act[l], I[lane]);
+        out = lane < nout ? act_fwd_rt(net.act[l], cur) : 0.0f;
       } else if (net.kind[l] == PB_DENSE) {
-        if (lane < nout) {
-          const float *w = sm + net.wt_off[l] + lane;
-          float acc = w[nin * kWarpPitch];  // the accumulator starts at the bias
-          for (int i = 0; i < nin; ++i) acc = fmaf(w[i * kWarpPitch], I[i], acc);
-          O[lane] = acc;
-        }
+        const float *w = sm + net.wt_off[l] + lane;
+        // the accumulator starts at the bias
+        out = warp_dense_fwd(w, nin, cur, lane < nout ? w[nin * kWarpPitch] : 0.0f, lane < nout);
       } else {  // softmax
-        float m = lane < nin ? I[lane] : -INFINITY;
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float p = lane < nin ? ref_exp(I[lane] - m) : 0.0f;
-        gs[lane] = p;
-        __syncwarp();
+        float m = lane < nin ? cur : -INFINITY;
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+        const float p = lane < nin ? ref_exp(cur - m) : 0.0f;
         float sum = 0.0f;
-        for (int i = 0; i < nin; ++i) sum += gs[i];
-        if (lane < nout) O[lane] = p / sum;
+        for (int i = 0; i < nin; ++i) sum += __shfl_sync(kFull, p, i);
+        out = lane < nout ? p / sum : 0.0f;
       }
-      __syncwarp();
+      cur = out;
+      acts[(l + 1) * 32 + lane] = out;              // read back by this lane only
     }
     // ---- dE/dO (error_layer.cc:81-91): lane k holds the gradient of output k -----------
     float g = 0.0f;
-    if (lane < net.n_out) {
-      const float o = acts[net.n_layers * 32 + lane];
-      g = net.loss == PB_MEAN_SQUARED ? o - e_cur : -1.0f * (e_cur * (1.0f / (o + kRefEps)));
-    }
+    if (lane < net.n_out)
+      g = net.loss == PB_MEAN_SQUARED ? cur - e_cur : -1.0f * (e_cur * (1.0f / (cur + kRefEps)));
     // ---- reverse loop -----------------------------------------------------------
-    for (int l = net.n_layers - 1; l >= 0; --l) {
-      const float *I = acts + l * 32;
+#pragma unroll
+    for (int l = n_layers - 1; l >= 0; --l) {
+      const float in = acts[l * 32 + lane];         // this lane's input value of layer l
       const int nin = net.nin[l], nout = net.nout[l];
       if (net.kind[l] == PB_ACTIVATION) {
-        g = lane < nin ? act_bwd_rt(net.act[l], I[lane], g) : 0.0f;
+        g = lane < nin ? act_bwd_rt(net.act[l], in, g) : 0.0f;
       } else if (net.kind[l] == PB_DENSE) {
-        gs[lane] = lane < nout ? g : 0.0f;
-        __syncwarp();
         float ng = 0.0f;
-        if (lane < nin) {  // with the pre-update weights
-          const float *w = sm + net.wt_off[l] + lane * kWarpPitch;
-          for (int o = 0; o < nout; ++o) ng = fmaf(gs[o], w[o], ng);
+        // row = this lane as an input (lanes past nin read row 0, their sum is dropped)
+        const float *wr = sm + net.wt_off[l] + (lane < nin ? lane : 0) * kWarpPitch;
+        for (int o0 = 0; o0 < nout; o0 += 8) {       // with the pre-update weights
+          float wv[8], gv[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int o = min(o0 + k, nout - 1);
+            wv[k] = wr[o];
+            gv[k] = __shfl_sync(kFull, g, o);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (o0 + k < nout) ng = fmaf(gv[k], wv[k], ng);
         }
-        __syncwarp();
-        if (lane < nout) {
-          float *w = sm + net.wt_off[l] + lane;
-          for (int i = 0; i < nin; ++i) w[i * kWarpPitch] = w[i * kWarpPitch] - lr * (g * I[i]);
-          w[nin * kWarpPitch] = w[nin * kWarpPitch] - lr * g;
+        if (lane >= nin) ng = 0.0f;
+        __syncwarp();                                // every row is read before any column moves
+        float *w = sm + net.wt_off[l] + (lane < nout ? lane : 0);   // column = this lane as an output
+        const float bias_old = w[nin * kWarpPitch];
+        for (int i0 = 0; i0 < nin; i0 += 8) {
+          float wv[8], xv[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = min(i0 + k, nin - 1);
+            wv[k] = w[i * kWarpPitch];
+            xv[k] = __shfl_sync(kFull, in, i);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (lane < nout && i0 + k < nin) w[(i0 + k) * kWarpPitch] = wv[k] - lr * (g * xv[k]);
         }
+        if (lane < nout) w[nin * kWarpPitch] = bias_old - lr * g;
+        __syncwarp();                                // columns visible to the next row reads
         g = ng;
-        __syncwarp();
       } else {  // softmax: dI[k] = sum_i (O_i * (delta_ik - O_k)) * G_i, ascending i
-        const float *O = I + 32;
-        gs[lane] = lane < nout ? g : 0.0f;
-        __syncwarp();
+        const float ok = acts[(l + 1) * 32 + lane];
         float acc = 0.0f;
-        if (lane < nin) {
-          const float ok = O[lane];
-          for (int i = 0; i < nout; ++i) acc += (O[i] * (((i == lane) ? 1.0f : 0.0f) - ok)) * gs[i];
+        for (int i = 0; i < nout; ++i) {
+          const float oi = __shfl_sync(kFull, ok, i), gi = __shfl_sync(kFull, g, i);
+          acc += (oi * (((i == lane) ? 1.0f : 0.0f) - ok)) * gi;
         }
-        g = acc;
-        __syncwarp();
+        g = lane < nin ? acc : 0.0f;
       }
     }
   }
-  for (int l = 0; l < net.n_layers; ++l) {
+  __syncwarp();
+  for (int l = 0; l < n_layers; ++l) {
     if (net.kind[l] != PB_DENSE) continue;
     const int ld = net.nin[l] + 1;
     for (int idx = lane; idx < net.nout[l] * ld; idx += 32) {
@@ -254,6 +292,22 @@ train_warp_kernel(const SmallNet net, float *__restrict__ W_global, const float 
       W_global[net.w_off[l] + idx] = sm[net.wt_off[l] + i * kWarpPitch + o];
     }
   }
+}
+
+typedef void (*warp_kernel_fn)(const SmallNet, float *, const float *, const float *, const float *,
+                               long long);
+warp_kernel_fn warp_kernel_for(int n_layers) {
+  switch (n_layers) {
+    case 1: return train_warp_kernel<1>;
+    case 2: return train_warp_kernel<2>;
+    case 3: return train_warp_kernel<3>;
+    case 4: return train_warp_kernel<4>;
+    case 5: return train_warp_kernel<5>;
+    case 6: return train_warp_kernel<6>;
+    case 7: return train_warp_kernel<7>;
+    case 8: return train_warp_kernel<8>;
+  }
+  return train_warp_kernel<0>;
 }
 
 }  // namespace
@@ -297,16 +351,12 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
   net.wt_total = (int)wt_total;
   // networks no wider than a warp run the one-warp kernel
   if (max_io <= 32) {
-    const size_t wsmem = sizeof(float) * (size_t)(wt_total + (n_layers + 1) * 32 + 32);
+    const size_t wsmem = sizeof(float) * (size_t)(wt_total + (n_layers + 1) * 32);
     if (wsmem <= 200 * 1024) {
-      static size_t wconfigured = 0;
-      if (wsmem > 48 * 1024 && wsmem > wconfigured) {
-        PB_CUDA(cudaFuncSetAttribute(train_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)wsmem));
-        wconfigured = wsmem;
-      }
-      train_warp_kernel<<<1, 32, wsmem, ctx->stream>>>(net, weights, lr, d_ins, d_expected,
-                                                       (long long)n_samples);
+      warp_kernel_fn kern = warp_kernel_for(n_layers);
+      if (wsmem > 48 * 1024)
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      kern<<<1, 32, wsmem, ctx->stream>>>(net, weights, lr, d_ins, d_expected, (long long)n_samples);
       PB_LAUNCHED(ctx);
       return 0;
     }

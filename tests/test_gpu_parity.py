@@ -460,30 +460,26 @@ def test_train_loop_one_warp_kernel(ctx, name, monkeypatch):
     util.assert_close(util.read_product_weights(net, S), w_ref, f"{name} one-warp TrainLoop")
 
 
-@pytest.mark.parametrize("name", SPECS)
-def test_train_loop_cooperative_kernel(ctx, name, monkeypatch):
-    """PB_TRAIN_COOP=1: strict per-sample SGD of any layer list as one cooperative persistent
-    kernel (train_coop.cu: grid-stride phases separated by grid barriers), 12 dependent
-    steps against the oracle's Train loop."""
-    monkeypatch.setenv("PB_TRAIN_COOP", "1")
-    monkeypatch.setenv("PB_TRAIN_SMALL", "0")
-    spec = po.spec_text(name)
-    S = po.RestatedNet(spec)
-    R = checker(name)
-    model, loss = util.architecture_from_spec(spec)
-    rng = np.random.default_rng(zlib.crc32(name.encode()) + 17)
-    w0 = util.xavier_like(S, rng)
-    n = 12
-    xs = util.f32(rng.normal(0, 1, (n, S.n_in)))
-    es = util.f32(rng.uniform(0, 1, (n, S.n_out)))
-    lr = 0.02
-    net = pb.Nnet(model, pb.NoWeightInit, loss)
-    net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
-    util.load_product_weights(net, S, w0)
-    w_ref = w0.copy()
-    R.train_loop(xs.copy(), es.copy(), w_ref, lr)
-    net.TrainLoop(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), n)
-    util.assert_close(util.read_product_weights(net, S), w_ref, f"{name} cooperative TrainLoop")
+@pytest.mark.parametrize("switches", [
+    {"PB_CONV_WT": "0"},          # convolution forward / input gradient: conv_umma.cu kernels
+    {"PB_WGRAD_UMMA": "0"},       # weight gradient: mma.sync kernels for all three layers
+    {"PB_WGRAD_UMMA": "0", "PB_WGRAD_MMA": "0"},   # weight gradient: FFMA kernels
+    {"PB_DISABLE_UMMA": "1"},     # no tensor-core kernel anywhere
+    {"PB_DISABLE_FUSION": "1"},   # layer-by-layer plan
+    {"PB_STEP_GRAPHS": "0"},      # eager steps
+    {"PB_STEP_CHAIN": "0"},       # no programmatic dependent launches
+    {"PB_TRAIN_SMALL": "0"},      # per-sample loop as a replayed graph
+], ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
+def test_library_switches(switches):
+    """Every environment switch of the library selects a path that is correct on its own:
+    the same oracle comparison (tests/fallback_worker.py) in a fresh process per switch set."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **switches)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fallback_worker.py")],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0 and "switches ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
 
 
 def _pool_routing(layer_values, L_pool):
