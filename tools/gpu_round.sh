@@ -9,11 +9,9 @@ mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1
 echo "pytest rc=$?" | tee -a $OUT/pytest_gpu_$TAG.log
 tail -3 $OUT/pytest_gpu_$TAG.log
-timeout 200 python tools/chain_check.py 100 1024 > $OUT/chain_check_$TAG.log 2>&1
-echo "chain_check rc=$?"; tail -1 $OUT/chain_check_$TAG.log
-python bench.py --steps 20 --warmup 3 --table $OUT/table_$TAG.json > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+python bench.py --steps 20 --warmup 3 --no-other-configs --table $OUT/table_$TAG.json > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 echo "bench rc=$?"; cat $OUT/bench_$TAG.json
-BENCH_SHORT="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+BENCH_SHORT="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs --min-seconds 0 --max-blocks 1"
 $BENCH_SHORT > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv \
     --log-file $OUT/launches_$TAG.csv $BENCH_SHORT > $OUT/ncu_launches_$TAG.log 2>&1

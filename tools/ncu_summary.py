@@ -80,19 +80,17 @@ def main():
         import json
         import re
         rows = list(csv.DictReader(open(full)))
+        FW, BW = "evaluate+activation+pool (tcgen05)", "input_delta+activation+pool backward (tcgen05)"
         label_of = [
-            (r"conv_wgrad_ws_kernel<5, 5, 4, 32", "convolution_layer_1:weight_update"),
-            (r"conv_wgrad_ws_kernel<5, 5, 4, 16", "convolution_layer_4:weight_update"),
-            (r"conv_wgrad_ws_kernel<5, 5, 4, 8", "convolution_layer_7:weight_update"),
-            (r"conv_wgrad_mma_rgb_kernel<unnamed>::NCfg<3, 16, 32>", "convolution_layer_1:weight_update"),
-            (r"conv_wgrad_mma_kernel<unnamed>::WCfg<16, 20, 16>", "convolution_layer_4:weight_update"),
-            (r"conv_wgrad_mma_kernel<unnamed>::WCfg<20, 20, 8>", "convolution_layer_7:weight_update"),
-            (r"UCfg<3, 16, 32, 32, 5, 0, 0>, 2>", "convolution_layer_1:evaluate+activation+pool (tcgen05)"),
-            (r"UCfg<16, 20, 16, 16, 5, 0, 0>, 2>", "convolution_layer_4:evaluate+activation+pool (tcgen05)"),
-            (r"UCfg<20, 20, 8, 8, 5, 0, 0>, 2>", "convolution_layer_7:evaluate+activation+pool (tcgen05)"),
-            (r"UCfg<16, 3, 32, 32, 5, 1, 1>", "convolution_layer_1:input_delta"),
-            (r"UCfg<20, 16, 16, 16, 5, 1, 0>", "convolution_layer_4:input_delta"),
-            (r"UCfg<20, 20, 8, 8, 5, 1, 0>", "convolution_layer_7:input_delta"),
+            (r"conv_wgrad_mma_rgb_kernel", "convolution_layer_1:weight_update"),
+            (r"conv_wgrad_umma_kernel<unnamed>::GCfg<16, 20, 16,", "convolution_layer_4:weight_update"),
+            (r"conv_wgrad_umma_kernel<unnamed>::GCfg<20, 20, 8,", "convolution_layer_7:weight_update"),
+            (r"UCfg<3, 16, 32, 32, 5, 0, 0>, 2>", "convolution_layer_1:" + FW),
+            (r"TCfg<16, 20, 16, 4, 0>, 2>", "convolution_layer_4:" + FW),
+            (r"TCfg<20, 20, 8, 4, 0>, 2>", "convolution_layer_7:" + FW),
+            (r"UCfg<16, 3, 32, 32, 5, 1, 1>, 2>", "convolution_layer_1:" + BW),
+            (r"TCfg<20, 16, 16, 4, 1>, 2>", "convolution_layer_4:" + BW),
+            (r"TCfg<20, 20, 8, 4, 1>, 2>", "convolution_layer_7:" + BW),
         ]
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         traffic = {}
@@ -104,11 +102,12 @@ def main():
                 if m and v:
                     total += float(v.replace(",", "")) * unit.get(m.group(2), 1.0)
             for pat, label in label_of:
-                if pat in name:
+                if pat in name.replace("(anonymous namespace)", "<unnamed>"):
                     traffic[label] = total
         if traffic:
             traffic["_source"] = f"ncu --set full capture {tag} (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
             json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+            json.dump(traffic, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
     # the tensor-core GEMM configurations (wide MLP, YOLOv1): full captures + bench lines
     for kind in ("dense", "yolo"):
         rp = os.path.join(G, f"prof_{kind}_{tag}.ncu-rep")
