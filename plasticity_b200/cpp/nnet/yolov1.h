@@ -87,6 +87,13 @@ class Yolov1 {
     net_.Train(image, expected);
   }
 
+  // One gradient-sum minibatch step over `batch` samples stored back to back (the batched
+  // counterpart of TrainSample: Nnet::BatchTrain semantics, nnet.h:617-669).
+  void TrainBatch(std::unique_ptr<compute::ClBuffer> &images,
+                  std::unique_ptr<compute::ClBuffer> &expected, size_t batch) {
+    net_.BatchTrain(images, expected, batch);
+  }
+
   Nnet &net() { return net_; }
 
  private:

@@ -219,6 +219,8 @@ int conv_input_delta(pb_context *ctx, const pb_layer_desc *l, const float *W, co
   if (batch >= kTiledMinBatch) {
     int rc = conv_input_delta_umma(ctx, l, W, G, dI, batch);
     if (rc >= 0) return rc;
+    rc = conv_input_delta_gemm_umma(ctx, l, W, G, dI, batch);
+    if (rc >= 0) return rc;
     rc = conv_input_delta_tiled(ctx, l, W, G, dI, batch);
     if (rc >= 0) return rc;
   }
@@ -233,6 +235,8 @@ int conv_weight_update(pb_context *ctx, const pb_layer_desc *l, const float *I,
     int rc = conv_weight_update_umma(ctx, l, I, W, G, out, lr, mode, batch);
     if (rc >= 0) return rc;
     rc = conv_weight_update_mma(ctx, l, I, W, G, out, lr, mode, batch);
+    if (rc >= 0) return rc;
+    rc = conv_weight_update_gemm_umma(ctx, l, I, W, G, out, lr, mode, batch);
     if (rc >= 0) return rc;
     rc = conv_weight_update_tiled(ctx, l, I, W, G, out, lr, mode, batch);
     if (rc >= 0) return rc;

@@ -15,6 +15,14 @@
 // pre-pass, so the B producer is the plain aligned float4 path.  The epilogue adds the
 // bias and writes [b][oc][pixel] — lanes along the pixels, coalesced — and can apply
 // the following ActivationLayer in the same pass (second output).
+//
+// Input gradient (nnet/convolution_layer.cc:100-224) on the same policy, `bwd` set:
+//   dI[b,c,y,x] = sum_{oc,fy,fx} Wk[oc,c,fy,fx] * G[b,oc,(y+p-fy)/s,(x+p-fx)/s]
+// (terms whose quotient is not integral or out of range vanish).  M = (sample, INPUT pixel),
+// N = input channel, K = (tap, output channel): the gather reads the gradient planes at the
+// transposed coordinates and the filters are re-tiled as [c][tap][oc].  Envelope: odd filters
+// with pad == filter/2 (every YOLOv1 layer), where the reference's centre guard (:209) is the
+// range check above; output-channel counts that are multiples of 16.
 #include "umma_gemm.cuh"
 
 namespace pb {
@@ -39,8 +47,29 @@ struct ConvArgs : GemmCore {
   // ROW of one channel per 8 k values (tap_yx[fy*C + ic] = fy << 8 | ic): a thread reads 8
   // consecutive input floats per row instead of gathering taps one by one.
   int korder;
+  // bwd: the gathered tensor is the gradient (C = its channels = the layer's filters, H x W =
+  // the layer's OUTPUT extent), OH x OW = the layer's input extent, OC = its input channels
+  int bwd;
   uint16_t tap_yx[kMaxTaps];
 };
+
+// Input gradient: Wk[c][tap*ICP + oc] = Wref[oc][c][tap]; bias[] = 0.
+__global__ void retile_filters_bwd_kernel(const float *__restrict__ Wref, float *__restrict__ Wk,
+                                          float *__restrict__ bias, int OC, int C, int taps,
+                                          int ICP, int Kp) {
+  const int64_t total = (int64_t)C * Kp;
+  const int64_t kref1 = (int64_t)C * taps + 1;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < C;
+       t += (int64_t)gridDim.x * blockDim.x)
+    bias[t] = 0.0f;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / Kp;
+    const int k = (int)(t - c * Kp);
+    const int tap = k / ICP, oc = k - tap * ICP;
+    Wk[t] = (tap < taps && oc < OC) ? Wref[oc * kref1 + c * taps + tap] : 0.0f;
+  }
+}
 
 // Wk[oc][tap*ICP + ic] = Wref[oc][ic][tap], zero in the padding.
 __global__ void retile_filters_kernel(const float *__restrict__ Wref, float *__restrict__ Wk,
@@ -85,12 +114,37 @@ struct ConvPolicy {
       const int ohw = g.OH * g.OW;
       const int b = mm / ohw, pix = mm - b * ohw;
       const int r = pix / g.OW, c = pix - r * g.OW;
+      if (g.bwd) {
+        iy0 = r + g.pad;   // gradient row = (iy0 - fy) / stride
+        ix0 = c + g.pad;
+        base_off = (int64_t)b * g.C * g.H * g.W;
+        return;
+      }
       iy0 = r * g.stride - g.pad;
       ix0 = c * g.stride - g.pad;
       base_off = (int64_t)b * g.C * g.H * g.W + (int64_t)iy0 * g.W + ix0;
     }
     __device__ __forceinline__ void load(const Args &g, int ks, int) {
       const int64_t hw = (int64_t)g.H * g.W;
+      if (g.bwd) {
+        // one tap per stage, 16 consecutive gradient channels (ICP is a multiple of 16)
+        const int per = g.ICP >> 4;
+        const int tap = ks / per, icb = ks - tap * per;
+        const int yx = g.tap_yx[min(tap, kMaxTaps - 1)];
+        const int dy = iy0 - (yx >> 8), dx = ix0 - (yx & 255);
+        const int qy = dy / g.stride, qx = dx / g.stride;
+        const bool ok = m_ok && tap < g.taps && dy >= 0 && dx >= 0 && qy * g.stride == dy &&
+                        qx * g.stride == dx && qy < g.H && qx < g.W;
+        const float *q = g.In + base_off + (int64_t)(icb * 16) * hw + (int64_t)qy * g.W + qx;
+        if (ok) {
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk, q += hw) v[kk] = __ldg(q);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) v[kk] = 0.0f;
+        }
+        return;
+      }
       if (g.korder == 1) {
         // two filter rows (fy, ic) per stage, 8 consecutive input columns each
         const int n_rows = g.FH * g.C;
@@ -262,6 +316,40 @@ int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float
   g.stride = (int)l->stride; g.pad = (int)l->padding;
   g.ICP = (int)ICP; g.taps = (int)taps; g.Kp = Kp;
   return launch_gemm<ConvPolicy>(ctx, g, (int)M, (int)OC, Kp);
+}
+
+// Input gradient on the same kernel; -1 outside the envelope.
+int conv_input_delta_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *W,
+                               const float *G, float *dI, int64_t batch) {
+  if (!umma_gemm_enabled()) return -1;
+  const int64_t C = l->depth, OC = l->num_filters;
+  const int64_t OW = conv_out_w(l), OH = conv_out_h(l);
+  const int64_t taps = l->filter_width * l->filter_height;
+  if (OC % 16 != 0 || !(l->filter_width & 1) || !(l->filter_height & 1) ||
+      l->padding != l->filter_width / 2 || l->padding != l->filter_height / 2)
+    return -1;
+  if (taps > kMaxTaps || l->filter_width > 255 || l->filter_height > 255) return -1;
+  const int64_t K = taps * OC, M = batch * l->height * l->width;
+  if (M <= 0 || C <= 0) return 0;
+  if (M * C * K < ((int64_t)1 << 26) || M >= ((int64_t)1 << 31) - BM || C * (K + BK) >= ((int64_t)1 << 31))
+    return -1;
+  const int Kp = pb_div_up(K, BK) * BK;
+  const size_t bias_off = ((size_t)C * Kp + 3) & ~(size_t)3;
+  if (ensure_aux(ctx, bias_off + (size_t)C + 16)) return 1;
+  retile_filters_bwd_kernel<<<pb_ew_grid(ctx, C * Kp, 256), 256, 0, ctx->stream>>>(
+      W, ctx->aux, ctx->aux + bias_off, (int)OC, (int)C, (int)taps, (int)OC, Kp);
+  PB_LAUNCHED(ctx);
+  ConvArgs g{};
+  g.In = G; g.Wk = ctx->aux; g.bias = ctx->aux + bias_off; g.Out = dI; g.Out2 = nullptr;
+  g.act = PB_IDENTITY; g.korder = 0; g.bwd = 1;
+  for (int t = 0; t < (int)taps; ++t)
+    g.tap_yx[t] = (uint16_t)(((t / l->filter_width) << 8) | (t % l->filter_width));
+  g.C = (int)OC; g.H = (int)OH; g.W = (int)OW;            // the gathered tensor: the gradient
+  g.OC = (int)C; g.OH = (int)l->height; g.OW = (int)l->width;
+  g.FH = (int)l->filter_height; g.FW = (int)l->filter_width;
+  g.stride = (int)l->stride; g.pad = (int)l->padding;
+  g.ICP = (int)OC; g.taps = (int)taps; g.Kp = Kp;
+  return launch_gemm<ConvPolicy>(ctx, g, (int)M, (int)C, Kp);
 }
 
 }  // namespace pb

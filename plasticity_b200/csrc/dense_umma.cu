@@ -150,6 +150,112 @@ bool worth_it(int64_t M, int64_t N, int64_t K) {
          K < (1 << 30);
 }
 
+// ---- convolution weight gradient as a GEMM with gathered operands ------------------------
+// (nnet/convolution_layer.cc:226-270, any filter / stride / padding / channel count)
+//   g[oc][c][fy][fx] = sum_{b,r,q} G[b,oc,r,q] * In0[b,c,r*s-p+fy,q*s-p+fx]
+// M = filter, N = (channel, tap) in the reference's own weight order, K = (sample, output
+// pixel): C is the filter-block matrix itself (row pitch = taps*C + 1), so the epilogue is the
+// dense SGD update.  A = the gradient, one filter row per thread, k runs along the pixels of a
+// plane and on into the next sample; B = the im2col matrix, never materialised: one (channel,
+// tap) row per thread whose k walk is a walk along the image row (zero outside the image).
+struct ConvWgradArgs : DenseArgs {
+  const float *G, *In;
+  int OCn, Cn, H, W, OH, OW, FW, taps, stride, pad, P;
+};
+
+struct ConvWgradPolicy : DensePolicy<OP_MN, OP_MN, true> {
+  using Args = ConvWgradArgs;
+  static constexpr int kMinBN = 128;
+  struct A : MatrixOperand<OP_MN, BM, LA> {
+    int oc;
+    bool row_ok;
+    __device__ __forceinline__ void init(const Args &g) { this->setup(nullptr, 0, g.M, g.K, BM); }
+    __device__ __forceinline__ void tile(const Args &g, int t, int p) {
+      oc = t * BM + p;
+      row_ok = oc < g.M;
+    }
+    __device__ __forceinline__ void load(const Args &g, int ks, int) {
+      const int k0 = ks * BK;
+      int b = k0 / g.P, pix = k0 - b * g.P;
+      const float *q = g.G + ((int64_t)b * g.OCn + (row_ok ? oc : 0)) * g.P + pix;
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        this->v[kk] = (row_ok && k0 + kk < g.K) ? __ldg(q) : 0.0f;
+        ++q;
+        if (++pix == g.P) {   // next sample: skip the other filters' planes
+          pix = 0;
+          q += (int64_t)(g.OCn - 1) * g.P;
+        }
+      }
+    }
+  };
+  template <int BN_T>
+  struct B : MatrixOperand<OP_MN, BN_T, BN_T + 2> {
+    static constexpr int H = BN_T / kGroupThreads;
+    int plane[H], fy[H], fx[H];
+    bool n_ok[H];
+    __device__ __forceinline__ void init(const Args &g) { this->setup(nullptr, 0, g.N, g.K, g.mma_n); }
+    __device__ __forceinline__ void tile(const Args &g, int t, int p) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const int n = t * BN_T + p + h * kGroupThreads;
+        n_ok[h] = n < g.N && h * kGroupThreads < this->rows_active;
+        const int nn = n_ok[h] ? n : 0;
+        const int c = nn / g.taps, tap = nn - c * g.taps;
+        fy[h] = tap / g.FW - g.pad;
+        fx[h] = tap % g.FW - g.pad;
+        plane[h] = c * g.H * g.W;
+      }
+    }
+    __device__ __forceinline__ void load(const Args &g, int ks, int) {
+      const int k0 = ks * BK;
+      int b = k0 / g.P;
+      const int pix = k0 - b * g.P;
+      int r = pix / g.OW, q = pix - r * g.OW;
+      int64_t sample = (int64_t)b * g.Cn * g.H * g.W;
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const bool k_ok = k0 + kk < g.K;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const int iy = r * g.stride + fy[h], ix = q * g.stride + fx[h];
+          const bool ok = k_ok && n_ok[h] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
+          this->v[4 * (H * (kk >> 2) + h) + (kk & 3)] =
+              ok ? __ldg(g.In + sample + plane[h] + iy * g.W + ix) : 0.0f;
+        }
+        if (++q == g.OW) {
+          q = 0;
+          if (++r == g.OH) {
+            r = 0;
+            sample += (int64_t)g.Cn * g.H * g.W;
+          }
+        }
+      }
+    }
+  };
+};
+
+// bias of filter oc: sum over samples and pixels of G[b][oc][.], one block per filter,
+// fixed summation order (thread-strided partial sums, then a shared-memory tree)
+__global__ void conv_bias_update_kernel(const float *__restrict__ G, const float *W, float *out,
+                                        const float *__restrict__ lr, int OCn, int P, int64_t batch,
+                                        int64_t K1, int mode) {
+  __shared__ float red[256];
+  const int oc = blockIdx.x;
+  float acc = 0.0f;
+  for (int64_t b = 0; b < batch; ++b) {
+    const float *g = G + (b * OCn + oc) * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) acc += g[i];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) apply_update(mode, out, W, (int64_t)oc * K1 + K1 - 1, lr[0], red[0]);
+}
+
 }  // namespace
 
 int dense_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
@@ -186,6 +292,32 @@ int dense_weight_update_umma(pb_context *ctx, const pb_layer_desc *l, const floa
   if (launch_gemm<DensePolicy<OP_MN, OP_MN, true>>(ctx, g, (int)nout, (int)in, (int)batch)) return 1;
   dense_bias_update_kernel<<<pb_div_up(nout, 128), 128, 0, ctx->stream>>>(G, W, out, lr, (int)in,
                                                                          (int)nout, batch, mode);
+  PB_LAUNCHED(ctx);
+  return 0;
+}
+
+// Convolution weight gradient + SGD update for any shape on the tensor cores; -1 when the
+// product is too small to be worth it (or PB_DISABLE_UMMA=1).
+int conv_weight_update_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                                 const float *Wt, const float *G, float *out, const float *lr,
+                                 int mode, int64_t batch) {
+  const int64_t C = l->depth, OC = l->num_filters;
+  const int64_t OW = conv_out_w(l), OH = conv_out_h(l), P = OW * OH;
+  const int64_t taps = l->filter_width * l->filter_height;
+  const int64_t N = C * taps, K = batch * P, K1 = N + 1;
+  if (!umma_gemm_enabled() || !worth_it(OC, N, K) || K >= ((int64_t)1 << 31) - BK ||
+      C * l->height * l->width >= ((int64_t)1 << 31))
+    return -1;
+  ConvWgradArgs g{};
+  g.K = (int)K;
+  g.epi = EPI_UPDATE; g.C = out; g.ldc = K1; g.Wold = Wt; g.lr = lr; g.mode = mode;
+  g.G = G; g.In = I;
+  g.OCn = (int)OC; g.Cn = (int)C; g.H = (int)l->height; g.W = (int)l->width;
+  g.OH = (int)OH; g.OW = (int)OW; g.FW = (int)l->filter_width; g.taps = (int)taps;
+  g.stride = (int)l->stride; g.pad = (int)l->padding; g.P = (int)P;
+  if (launch_gemm<ConvWgradPolicy>(ctx, g, (int)OC, (int)N, (int)K)) return 1;
+  conv_bias_update_kernel<<<(unsigned)OC, 256, 0, ctx->stream>>>(G, Wt, out, lr, (int)OC, (int)P, batch,
+                                                                 K1, mode);
   PB_LAUNCHED(ctx);
   return 0;
 }

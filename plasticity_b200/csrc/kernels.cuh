@@ -118,6 +118,15 @@ int conv_act_pool_input_delta_wt(pb_context *ctx, const pb_layer_desc *conv, int
 int conv_evaluate_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *I,
                             const float *W, float *O, float *O2, int act, int64_t batch);
 
+// the same skeleton for the backward pass of any convolution: input gradient (conv_gemm_umma.cu,
+// odd filters with pad == filter/2, filter counts that are multiples of 16) and weight gradient
+// + SGD update (dense_umma.cu, any shape); -1 outside the envelope.
+int conv_input_delta_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *W,
+                               const float *G, float *dI, int64_t batch);
+int conv_weight_update_gemm_umma(pb_context *ctx, const pb_layer_desc *l, const float *I,
+                                 const float *Wt, const float *G, float *out, const float *lr,
+                                 int mode, int64_t batch);
+
 // train_small.cu: n per-sample SGD steps of a small all-dense network as ONE persistent
 // single-CTA kernel (weights, activations and gradients in shared memory); -1 outside the
 // envelope (the graph-replayed layer-by-layer loop then runs).

@@ -100,3 +100,14 @@ class Yolov1:
         """One per-sample SGD step (Nnet::Train) on the squared error of the 7x7x30 grid."""
         self.net_.Train(self.net_.MakeBuffer(np.asarray(image, dtype=np.float64).reshape(-1)),
                         self.net_.MakeBuffer(np.asarray(expected, dtype=np.float64).reshape(-1)))
+
+    def TrainBatch(self, images, expected, batch: int) -> None:
+        """One gradient-sum minibatch step (Nnet::BatchTrain semantics, nnet.h:617-669:
+        W <- W - lr * sum over the batch) — the batched counterpart of TrainSample: every
+        convolution's input gradient and weight gradient run on the tensor-core GEMM policies
+        (conv_gemm_umma.cu, dense_umma.cu)."""
+        bx = images if isinstance(images, N.ClBuffer) else self.net_.MakeBuffer(
+            np.asarray(images, dtype=np.float64).reshape(-1))
+        be = expected if isinstance(expected, N.ClBuffer) else self.net_.MakeBuffer(
+            np.asarray(expected, dtype=np.float64).reshape(-1))
+        self.net_.BatchTrain(bx, be, batch)
