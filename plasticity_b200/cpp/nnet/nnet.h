@@ -419,6 +419,11 @@ class Nnet {
   }
 
   static std::string FormatDouble(double v) {
+    if (!std::isfinite(v)) {  // not JSON: rapidjson's Writer::Double refuses it as well
+      std::cerr << "WeightsToString: non-finite weight (the network diverged); refusing to "
+                   "write an unloadable weight file" << std::endl;
+      std::exit(1);
+    }
     char buf[40];
     std::snprintf(buf, sizeof(buf), "%.17g", v);
     std::string s(buf);

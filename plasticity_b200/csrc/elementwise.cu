@@ -388,6 +388,47 @@ __global__ void softmax_bwd_kernel(const float *__restrict__ I, const float *__r
   }
 }
 
+// any n: the same arithmetic with the outputs staged in a global workspace ([sample][n]) instead
+// of shared memory; one CTA per sample.  For layers wider than the shared-memory path holds.
+__global__ void softmax_bwd_wide_kernel(const float *__restrict__ I, const float *__restrict__ G,
+                                        float *__restrict__ dI, float *__restrict__ O, int n,
+                                        int64_t batch) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int64_t b = blockIdx.x; b < batch; b += gridDim.x) {
+    const float *x = I + b * n, *g = G + b * n;
+    float *o = O + b * n;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, x[i]);
+    m = warp_max(m);
+    if (lane == 0) red[wib] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < nw; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float p = ref_exp(x[i] - m);
+      o[i] = p;
+      s += p;
+    }
+    s = warp_sum(s);
+    if (lane == 0) red[wib] = s;
+    __syncthreads();
+    s = 0.0f;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = o[i] / s;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      const float ok = o[k];
+      float acc = 0.0f;
+      for (int i = 0; i < n; ++i) acc += (o[i] * (((i == k) ? 1.0f : 0.0f) - ok)) * g[i];
+      dI[b * n + k] = acc;
+    }
+    __syncthreads();
+  }
+}
+
 int softmax_evaluate(pb_context *ctx, int64_t n, const float *I, float *O, int64_t batch) {
   if (n == 0 || batch == 0) return 0;
   const int T = 128;
@@ -406,7 +447,13 @@ int softmax_input_delta(pb_context *ctx, int64_t n, const float *I, const float 
     softmax_bwd_small_kernel<<<grid, T, 0, ctx->stream>>>(I, G, dI, (int)n, batch);
   } else {
     const size_t smem = (size_t)(T / 32) * 2 * n * sizeof(float);
-    if (smem > 200 * 1024) return fail("softmax: width too large for the shared-memory path");
+    if (smem > 200 * 1024) {
+      if (ensure_workspace(ctx, (size_t)batch * n)) return 1;
+      softmax_bwd_wide_kernel<<<(int)std::min<int64_t>(batch, (int64_t)ctx->num_sms * 4), 256, 0,
+                                ctx->stream>>>(I, G, dI, ctx->workspace, (int)n, batch);
+      PB_LAUNCHED(ctx);
+      return 0;
+    }
     if (smem > 48 * 1024)
       PB_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

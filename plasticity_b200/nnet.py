@@ -534,9 +534,15 @@ class Nnet:
         for i, layer in enumerate(self.model().layers):
             layers.append({"name": layer.LayerSuffix(), "index": i,
                            "weights": [float(w) for w in layer.weights]})
-        return json.dumps({"version": kWeightFileFormatVersion,
-                           "number_of_layers": len(layers), "layers": layers},
-                          separators=(",", ":"))
+        try:
+            # allow_nan=False: NaN / Infinity are not JSON; a diverged network must not write a
+            # file that neither implementation can load back (rapidjson's Writer refuses too)
+            return json.dumps({"version": kWeightFileFormatVersion,
+                               "number_of_layers": len(layers), "layers": layers},
+                              separators=(",", ":"), allow_nan=False)
+        except ValueError as exc:
+            raise L.PlasticityError("WeightsToString: non-finite weight (the network diverged); "
+                                    "refusing to write an unloadable weight file") from exc
 
     def LoadWeightsFromString(self, weight_string: str) -> bool:
         try:

@@ -482,6 +482,38 @@ def test_library_switches(switches):
     assert r.returncode == 0 and "switches ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
 
 
+def test_softmax_backward_wider_than_shared_memory(ctx):
+    """A softmax too wide for the per-warp shared-memory staging (n > 6400) takes the
+    global-workspace kernel; the forward pass accepts any width, so must the backward
+    (softmax_layer.cc:48-59).  Reference: the closed form of the same sum in fp64,
+    dI_k = O_k * (G_k - sum_i O_i G_i); the oracle's own O(n^3) loop is out of reach here."""
+    n, batch = 6500, 3
+    rng = np.random.default_rng(65)
+    I = util.f32(rng.normal(0, 2, (batch, n)))
+    G = util.f32(rng.normal(0, 1, (batch, n)))
+    desc = L.LayerDesc(kind=L.PB_SOFTMAX, n=n)
+    dI_, dG, dDI = Dev(ctx, I), Dev(ctx, G), Dev(ctx, np.zeros(batch * n))
+    L.call("pb_layer_input_delta", ctx, C.byref(desc), dI_.p, None, dG.p, dDI.p, batch)
+    z = (I - I.max(axis=1, keepdims=True)) * np.log(2.71828)
+    O = np.exp(z) / np.exp(z).sum(axis=1, keepdims=True)
+    want = O * (G - (O * G).sum(axis=1, keepdims=True))
+    util.assert_close(dDI.host().reshape(batch, n), want, "wide softmax input_delta")
+
+
+def test_weight_file_refuses_non_finite_weights(ctx):
+    """A diverged network must not write a weight file that neither implementation can load
+    back (NaN / Infinity are not JSON; rapidjson's Writer refuses them, nnet.h:761-789)."""
+    m = pb.Architecture(3)
+    m.AddDenseLayer(2)
+    net = pb.Nnet(m, pb.InitToOne, pb.MeanSquared)
+    assert net.LoadWeightsFromString(net.WeightsToString())
+    w = np.asarray(net.GetLayerWeights(1)).copy()
+    w[3] = np.inf
+    net.SetLayerWeights(1, w)
+    with pytest.raises(L.PlasticityError, match="non-finite"):
+        net.WeightsToString()
+
+
 def _pool_routing(layer_values, L_pool):
     """Per window of a max-pool layer: index of the first maximum, whether the maximum is
     unique, and the relative gap between the two largest values."""
