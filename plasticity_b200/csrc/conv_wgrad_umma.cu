@@ -483,10 +483,15 @@ int conv_weight_update_umma(pb_context *ctx, const pb_layer_desc *l, const float
   const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
   if (w == 16 && d == 16 && f == 20) return launch<GCfg<16, 20, 16, 16, false, 2, 8>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
   if (w == 8 && d == 20 && f == 20) return launch<GCfg<20, 20, 8, 8, false, 2, 8>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
-  // The RGB layer (3 -> 16 channels, N = 30) is bound by producing the gradient operand
-  // (80 rows x 40 columns x hi/lo per image row through shared memory and tcgen05.st): 77 us
-  // against 58 us of the mma.sync kernel of conv_wgrad_mma.cu, which therefore keeps it.
-  // (kept instantiable: GCfg<3, 16, 32, 16, true, 3, 6> is that configuration)
+  // The RGB layer (3 -> 16 channels) stays with the mma.sync kernel of conv_wgrad_mma.cu (58 us).
+  // Both tensor-memory mappings were built and measured on B200 and are bound by PRODUCING the
+  // tensor-memory operand with a handful of warps (LDS + split + tcgen05.st + wait::st per image
+  // row, ~350 cycles per row and lane quadrant against ~200 cycles of MMA issue):
+  //   gradient side in tensor memory (GCfg<3, 16, 32, 16, true, 3, 6>: 80 rows x 40 columns per
+  //   image row, hi|lo of the image stacked along N)                                   77 us
+  //   image side in tensor memory (75 rows = (c, fy, fx) x 32 columns, conflict-free tile
+  //   pitches 5 / 25 mod 32, hi|lo of the gradient stacked along N), 3 / 5 warps per
+  //   lane quadrant                                                                66 / 62 us
   return -1;
 }
 

@@ -448,6 +448,20 @@ template <class P>
 int launch_gemm(pb_context *ctx, const typename P::Args &g, int M, int N, int K) {
   if (N <= 64 && P::kMinBN <= 64) return launch_gemm_bn<P, 64>(ctx, g, M, N, K);
   if (N <= 128 && P::kMinBN <= 128) return launch_gemm_bn<P, 128>(ctx, g, M, N, K);
+  if (P::kMinBN <= 128) {
+    // Tile quantisation: a problem whose 128 x 256 tiles fill the last wave badly (sharded
+    // inference at a small per-GPU batch: 196 tiles on 148 SMs) runs on 128 x 128 tiles when
+    // that fills the SMs better by more than what the narrower tile costs (it re-stages A
+    // twice as often; ~0.88 of the wide tile's rate).
+    auto fill = [&](int bn) {
+      const int64_t tiles = (int64_t)pb_div_up(M, BM) * pb_div_up(N, bn);
+      if (tiles * 2 <= ctx->num_sms) return 0.0;  // split-K territory: leave it to the wide tile
+      const int64_t waves = (tiles + ctx->num_sms - 1) / ctx->num_sms;
+      return (double)tiles / (double)(waves * ctx->num_sms);
+    };
+    const double wide = fill(256), narrow = fill(128) * 0.88;
+    if (wide > 0.0 && narrow > wide * 1.05) return launch_gemm_bn<P, 128>(ctx, g, M, N, K);
+  }
   return launch_gemm_bn<P, 256>(ctx, g, M, N, K);
 }
 
