@@ -360,6 +360,10 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   } else if (warp == kMmaWarp) {
     // ---- MMA issuer ----------------------------------------------------------
     const bool leader = elect_one();
+#ifdef PB_UMMA_PROF
+    long long pt[3] = {0, 0, 0};
+    const long long pt_start = clock64();
+#endif
     constexpr uint32_t idesc1 = make_idesc(C::MT, C::N1), idesc2 = make_idesc(C::MT, C::N2);
     constexpr uint32_t a_hi32 = (uint32_t)C::P | (1u << 14);  // SBO = row pitch, version 1
     constexpr uint32_t b_hi32 = 8u | (1u << 14);              // SBO = 128 B
@@ -367,8 +371,17 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
+#ifdef PB_UMMA_PROF
+      long long t0_ = clock64();
+#endif
       mbar_wait(&a_full[s], ph);
+#ifdef PB_UMMA_PROF
+      pt[0] += clock64() - t0_; t0_ = clock64();
+#endif
       mbar_wait(&d_empty[s], ph ^ 1);
+#ifdef PB_UMMA_PROF
+      pt[1] += clock64() - t0_; t0_ = clock64();
+#endif
       tc_fence_after();
       // Descriptor arithmetic is warp-uniform (uniform datapath); only the
       // tcgen05 instructions themselves are predicated on the elected lane.
@@ -396,7 +409,15 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
         umma_commit(&d_full[s]);
       }
       __syncwarp();
+#ifdef PB_UMMA_PROF
+      pt[2] += clock64() - t0_;
+#endif
     }
+#ifdef PB_UMMA_PROF
+    if (blockIdx.x == 0 && lane == 0)
+      printf("conv_umma MMA warp (NS=%d BWD=%d ACT=%d): total %lld | wait a_full %lld, wait d_empty %lld, issue %lld, items %d\n",
+             (int)C::NS, (int)C::BWD, ACT, clock64() - pt_start, pt[0], pt[1], pt[2], it);
+#endif
   } else {
     // ---- epilogue: TMEM -> registers -> (+bias) -> global ---------------------
     int it = 0;
