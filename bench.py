@@ -570,6 +570,9 @@ def run_ours(args):
                  "fp32_peak_tflops_measured": tf.value * world,
                  "flop_per_sample": TRAIN_FLOP_PER_SAMPLE}
         whole["frac"] = whole["achieved_tflops"] / whole["fp32_peak_tflops_measured"]
+        # every convolution kernel of the step runs on the tensor pipe: the same work against
+        # the 3xTF32 peak (bf16 / 2 / 3), the denominator of `roofline`
+        whole["frac_of_3xtf32_tensor_peak"] = whole["achieved_tflops"] / (bf16_peak / 2 / 3 * world)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = reference_rate(np, 2, 1, args.ref_sample)
