@@ -97,9 +97,17 @@ class CudaCommandQueue : public CommandQueue {
         Need(kernel_name, a, 5);
         if (nw == 0 || (int64_t)global_size != nw)
           Die("enqueueKernel: " + kernel_name + " takes global size = number of weights");
-        // one work-item per weight: the sample count comes from the input buffer
-        const int64_t batch = nin > 0 ? (int64_t)a[0].size() / nin : 0;
-        if (batch < 1) Die("enqueueKernel: " + kernel_name + ": input buffer smaller than the layer");
+        // One work-item per weight: the global size says nothing about samples.  The
+        // reference's callers pass scratch buffers sized max_layer_output_size (nnet.h:86-97),
+        // i.e. LARGER than the layer; such a pair is one sample, exactly as the reference's
+        // kernel reads it.  A batch is recognised only when BOTH the input and the gradient
+        // buffer hold the same whole number of samples.
+        const int64_t by_in = nin > 0 ? (int64_t)a[0].size() / nin : 0;
+        const int64_t by_out = nout > 0 ? (int64_t)a[2].size() / nout : 0;
+        if (by_in < 1 || by_out < 1)
+          Die("enqueueKernel: " + kernel_name + ": input / gradient buffer smaller than the layer");
+        const bool whole = (int64_t)a[0].size() == by_in * nin && (int64_t)a[2].size() == by_out * nout;
+        const int64_t batch = (whole && by_in == by_out) ? by_in : 1;
         PB_CHECK_OK(pb_layer_weight_update(ctx_, l, Dev(a[0]), Dev(a[1]), Dev(a[2]), Dev(a[3]),
                                            Dev(a[4]), f.kind == 2 ? PB_NEW_WEIGHTS : PB_WEIGHT_DELTAS,
                                            batch));

@@ -252,6 +252,31 @@ def test_batch_train_fused_plan(ctx, name):
                               f"{name} fused BatchTrain step {step} max_batch={max_batch}")
 
 
+@pytest.mark.parametrize("B", [77, 149, 297])
+def test_batch_train_fused_plan_odd_batches(ctx, B):
+    """The fused step at batch sizes that are no multiple of anything the kernels tile by:
+    one item more than the SM count (149: one CTA walks two items, 147 walk one), a batch
+    just above the tensor-core threshold (77) and an odd multi-wave one (297)."""
+    name = "cifar"
+    spec = po.spec_text(name)
+    S = po.RestatedNet(spec)
+    R = checker(name)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(7000 + B)
+    w0 = util.xavier_like(S, rng)
+    lr = 0.002
+    es = util.f32(rng.uniform(0, 1, (B, S.n_out)))
+    xs = util.draw_with_pool_margin(S, rng, B, w0)
+    net = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=B)
+    net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+    util.load_product_weights(net, S, w0)
+    w_ref = w0.copy()
+    R.batch_train(xs.copy(), es.copy(), w_ref, lr)
+    util.assert_close(util.device_deltas(net, S, xs, es), w_ref - w0, f"B={B} deltas (delta-buffer pass)")
+    net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), B)
+    util.assert_close(util.read_product_weights(net, S), w_ref, f"B={B} weights (in-place step)")
+
+
 @pytest.mark.parametrize("layer", [1, 4, 7])
 def test_conv_persistent_pipeline_large_batch(ctx, layer):
     """The tensor-core convolution kernels are persistent (one CTA per SM walking
