@@ -176,7 +176,21 @@ conv_umma_kernel(const float *__restrict__ In, const float *__restrict__ Wt,
   float *w_raw = reinterpret_cast<float *>(a_s);
   // L2 loads (ld.global.cg): ahead of the dependency wait nothing may rely on this SM's L1
   // having been invalidated since the filters were last updated
-  for (int i = tid; i < NWT; i += blockDim.x) w_raw[i] = __ldcg(Wt + i);
+  {
+    // every load of the thread in flight before the first store (one L2 round trip)
+    constexpr int WL = (NWT + kThreads - 1) / kThreads;
+    float wv[WL];
+#pragma unroll
+    for (int k = 0; k < WL; ++k) {
+      const int i = tid + k * kThreads;
+      wv[k] = i < NWT ? __ldcg(Wt + i) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < WL; ++k) {
+      const int i = tid + k * kThreads;
+      if (i < NWT) w_raw[i] = wv[k];
+    }
+  }
   __syncthreads();
   for (int u = tid; u < C::B_UNITS; u += blockDim.x) {
     const int slot = u / C::N1, n = u - slot * C::N1;

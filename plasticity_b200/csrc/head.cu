@@ -35,7 +35,23 @@ head_kernel(const float *__restrict__ X, const float *__restrict__ W, const floa
   extern __shared__ float w_s[];  // [out][in+1], reference layout
   const int ld = in + 1;
   if (!early_w) chain_wait();  // chained launch, common.cuh
-  for (int i = threadIdx.x; i < out * ld; i += blockDim.x) w_s[i] = __ldcg(W + i);  // L2: see conv_umma.cu
+  {
+    // L2 loads (see conv_umma.cu), sixteen per thread in flight before the first store
+    const int nw = out * ld;
+    for (int base = 0; base < nw; base += 16 * 256) {
+      float wv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int i = base + threadIdx.x + k * 256;
+        wv[k] = i < nw ? __ldcg(W + i) : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int i = base + threadIdx.x + k * 256;
+        if (i < nw) w_s[i] = wv[k];
+      }
+    }
+  }
   __syncthreads();
   if (early_w) chain_wait();
   chain_release();
