@@ -348,18 +348,27 @@ struct NCfg {
   static_assert(SMEM <= 220 * 1024, "shared memory");
 };
 
-template <class C>
-__global__ void __launch_bounds__(C::THREADS + 32, 1)
+// ACT >= 0: the gradient tile is FORMED by the (then four) producer warps from the stored
+// convolution output O (passed as `G`) and the gradient Gp of the 2x2 max-pool's output behind
+// the activation - act_pool_bwd_kernel (elementwise.cu) value for value - so dE/d(conv output)
+// of the first convolution never travels through HBM.  nnet.cu uses it when nothing reads the
+// layer's input gradient (the network's first convolution: BatchTrain has no input_gradients
+// parameter, nnet/nnet.h:617-622).
+constexpr int kFormWarps = 4;
+template <class C, int ACT>
+__global__ void __launch_bounds__(C::THREADS + (ACT >= 0 ? 32 * kFormWarps : 32), 1)
 conv_wgrad_mma_rgb_kernel(const float *__restrict__ In, const float *__restrict__ G,
-                          float *__restrict__ partial, int batch, int samples_per_cta) {
+                          const float *__restrict__ Gp, float *__restrict__ partial, int batch,
+                          int samples_per_cta) {
   extern __shared__ __align__(16) float smem[];
+  constexpr int kProd = ACT >= 0 ? 32 * kFormWarps : 32, kAll = C::THREADS + kProd;
   const int tid = threadIdx.x, slice = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   __shared__ uint64_t full_bar[2], empty_bar[2];
-  for (int i = tid; i < C::MAIN_ELEMS; i += C::THREADS + 32) smem[i] = 0.0f;
+  for (int i = tid; i < C::MAIN_ELEMS; i += kAll) smem[i] = 0.0f;
   if (tid == 0) {
     for (int st = 0; st < 2; ++st) {
-      umma::mbar_init(&full_bar[st], 32);
+      umma::mbar_init(&full_bar[st], ACT >= 0 ? 2 * kProd : kProd);  // cp.async + plain arrivals
       umma::mbar_init(&empty_bar[st], C::WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -370,27 +379,72 @@ conv_wgrad_mma_rgb_kernel(const float *__restrict__ In, const float *__restrict_
   const int b0 = blockIdx.x * samples_per_cta;
   const int b1 = min(batch, b0 + samples_per_cta);
 
-  auto load = [&](int st, int b) {  // producer warp only
-    float *in_s = smem + st * C::STAGE, *g_s = in_s + C::IN_ELEMS;
-    const float *src = In + (int64_t)b * C::IC * C::S * C::S;
-    for (int e = lane; e < C::IC * C::S * C::S / 4; e += 32) {
-      const int x4 = e % (C::S / 4), r = e / (C::S / 4);
-      const int y = r % C::S, ic = r / C::S;
-      __pipeline_memcpy_async(in_s + ic * C::PLANE + (y + C::PADW) * C::PITCH + C::LEFT + 4 * x4,
-                              src + 4 * e, 16);
-    }
-    const float *gs = G + (int64_t)b * C::OC * C::S * C::S;
-    for (int e = lane; e < C::OC * C::S * C::S / 4; e += 32) {
-      const int q = e % (C::S * C::S / 4), oc = e / (C::S * C::S / 4);
-      __pipeline_memcpy_async(g_s + oc * C::GPLANE + 4 * q, gs + 4 * e, 16);
-    }
-  };
-  if (slice == C::WARPS) {
+  if (slice >= C::WARPS) {  // producers
+    const int pt = tid - C::THREADS;
     for (int b = b0; b < b1; ++b) {
       const int i = b - b0, st = i & 1;
       umma::mbar_wait(&empty_bar[st], ((i >> 1) & 1) ^ 1);
-      load(st, b);
-      cp_async_arrive(&full_bar[st]);
+      float *in_s = smem + st * C::STAGE, *g_s = in_s + C::IN_ELEMS;
+      const float *src = In + (int64_t)b * C::IC * C::S * C::S;
+      for (int e = pt; e < C::IC * C::S * C::S / 4; e += kProd) {
+        const int x4 = e % (C::S / 4), r = e / (C::S / 4);
+        const int y = r % C::S, ic = r / C::S;
+        __pipeline_memcpy_async(in_s + ic * C::PLANE + (y + C::PADW) * C::PITCH + C::LEFT + 4 * x4,
+                                src + 4 * e, 16);
+      }
+      if constexpr (ACT < 0) {
+        const float *gs = G + (int64_t)b * C::OC * C::S * C::S;
+        for (int e = pt; e < C::OC * C::S * C::S / 4; e += kProd) {
+          const int q = e % (C::S * C::S / 4), oc = e / (C::S * C::S / 4);
+          __pipeline_memcpy_async(g_s + oc * C::GPLANE + 4 * q, gs + 4 * e, 16);
+        }
+        cp_async_arrive(&full_bar[st]);
+      } else {
+        cp_async_arrive(&full_bar[st]);
+        // a thread owns two pool windows (2 rows x 4 columns) of every filter plane, four
+        // planes in flight (constant strides: one base address per thread)
+        constexpr int HS = C::S / 2, WQ = C::S / 4;
+        static_assert(HS * WQ == kProd && C::OC % 4 == 0, "one item per thread and plane");
+        const int xq = pt % WQ, orow = pt / WQ;
+        const float *o = G + (int64_t)b * C::OC * C::S * C::S + 2 * orow * C::S + 4 * xq;
+        const float *gp = Gp + (int64_t)b * C::OC * HS * HS + orow * HS + 2 * xq;
+        float *gd = g_s + 2 * orow * C::S + 4 * xq;
+#pragma unroll 1
+        for (int oc0 = 0; oc0 < C::OC; oc0 += 4) {
+          float4 o0[4], o1[4];
+          float2 gg[4];
+          int dst[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            o0[k] = *reinterpret_cast<const float4 *>(o + (oc0 + k) * C::S * C::S);
+            o1[k] = *reinterpret_cast<const float4 *>(o + (oc0 + k) * C::S * C::S + C::S);
+            gg[k] = *reinterpret_cast<const float2 *>(gp + (oc0 + k) * HS * HS);
+            dst[k] = (oc0 + k) * C::GPLANE;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 p0 = o0[k], p1 = o1[k];
+            const float a00 = act_fwd<ACT>(p0.x), a01 = act_fwd<ACT>(p0.y), a02 = act_fwd<ACT>(p0.z),
+                        a03 = act_fwd<ACT>(p0.w);
+            const float a10 = act_fwd<ACT>(p1.x), a11 = act_fwd<ACT>(p1.y), a12 = act_fwd<ACT>(p1.z),
+                        a13 = act_fwd<ACT>(p1.w);
+            const float m0 = fmaxf(fmaxf(a00, a01), fmaxf(a10, a11));
+            const float m1 = fmaxf(fmaxf(a02, a03), fmaxf(a12, a13));
+            float4 d0, d1;
+            d0.x = act_bwd<ACT>(p0.x, a00 < m0 ? 0.0f : gg[k].x);
+            d0.y = act_bwd<ACT>(p0.y, a01 < m0 ? 0.0f : gg[k].x);
+            d0.z = act_bwd<ACT>(p0.z, a02 < m1 ? 0.0f : gg[k].y);
+            d0.w = act_bwd<ACT>(p0.w, a03 < m1 ? 0.0f : gg[k].y);
+            d1.x = act_bwd<ACT>(p1.x, a10 < m0 ? 0.0f : gg[k].x);
+            d1.y = act_bwd<ACT>(p1.y, a11 < m0 ? 0.0f : gg[k].x);
+            d1.z = act_bwd<ACT>(p1.z, a12 < m1 ? 0.0f : gg[k].y);
+            d1.w = act_bwd<ACT>(p1.w, a13 < m1 ? 0.0f : gg[k].y);
+            *reinterpret_cast<float4 *>(gd + dst[k]) = d0;
+            *reinterpret_cast<float4 *>(gd + dst[k] + C::S) = d1;
+          }
+        }
+        umma::mbar_arrive(&full_bar[st]);
+      }
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
@@ -538,10 +592,10 @@ __global__ void wgrad_mma_rgb_reduce_kernel(const float *__restrict__ partial, i
   apply_update(mode, out, Wt, w, lr[0], acc);
 }
 
-template <class C>
-int launch_rgb(pb_context *ctx, const float *I, const float *Wt, const float *G, float *out,
-               const float *lr, int mode, int batch) {
-  auto kern = conv_wgrad_mma_rgb_kernel<C>;
+template <class C, int ACT>
+int launch_rgb(pb_context *ctx, const float *I, const float *Wt, const float *G, const float *Gp,
+               float *out, const float *lr, int mode, int batch) {
+  auto kern = conv_wgrad_mma_rgb_kernel<C, ACT>;
   static bool configured = false;
   if (!configured) {
     PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
@@ -551,7 +605,8 @@ int launch_rgb(pb_context *ctx, const float *I, const float *Wt, const float *G,
   const int spc = (batch + n_cta - 1) / n_cta;
   const int grid = (batch + spc - 1) / spc;
   if (ensure_workspace(ctx, (size_t)grid * C::ROW)) return 1;
-  PB_CUDA(launch_chained(ctx, kern, dim3(grid), dim3(C::THREADS + 32), C::SMEM, I, G,
+  PB_CUDA(launch_chained(ctx, kern, dim3(grid),
+                         dim3(C::THREADS + (ACT >= 0 ? 32 * kFormWarps : 32)), C::SMEM, I, G, Gp,
                          ctx->workspace, batch, spc));
   PB_LAUNCHED(ctx);
   PB_CUDA(launch_chained(ctx, wgrad_mma_rgb_reduce_kernel<C>, dim3(pb_div_up(C::ROW, 32)), dim3(256),
@@ -575,8 +630,40 @@ int conv_weight_update_mma(pb_context *ctx, const pb_layer_desc *l, const float 
   const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
   if (w == 16 && d == 16 && f == 20) return launch<WCfg<16, 20, 16>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
   if (w == 8 && d == 20 && f == 20) return launch<WCfg<20, 20, 8>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
-  if (w == 32 && d == 3 && f == 16) return launch_rgb<NCfg<3, 16, 32>>(ctx, I, Wt, G, out, lr, mode, (int)batch);
+  if (w == 32 && d == 3 && f == 16)
+    return launch_rgb<NCfg<3, 16, 32>, -1>(ctx, I, Wt, G, nullptr, out, lr, mode, (int)batch);
   return -1;
+}
+
+// The weight gradient of a (convolution, activation, 2x2 max-pool) block straight from the
+// convolution's stored output O and the gradient Gp of the pool's output; dE/d(conv output) is
+// formed inside the kernel and the convolution's input gradient is NOT computed (the caller
+// has no reader for it).  Returns -1 outside the envelope.
+int conv_act_pool_weight_update_mma(pb_context *ctx, const pb_layer_desc *l, int act,
+                                    const pb_layer_desc *pool, const float *I, const float *Wt,
+                                    const float *O, const float *Gp, float *out, const float *lr,
+                                    int mode, int64_t batch) {
+  static const bool on = [] {
+    const char *e = getenv("PB_DISABLE_UMMA"), *f = getenv("PB_WGRAD_MMA"), *h = getenv("PB_WGRAD_FORM");
+    return !(e && e[0] == '1') && !(f && f[0] == '0') && !(h && h[0] == '0');
+  }();
+  if (!on || l->stride != 1 || l->filter_width != 5 || l->filter_height != 5 || l->padding != 2 ||
+      l->width != l->height || batch < 64 || batch > (1 << 24))
+    return -1;
+  const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
+  if (pool->width != w || pool->height != w || pool->depth != f || pool->out_width * 2 != w ||
+      pool->out_height * 2 != w)
+    return -1;
+  if ((((uintptr_t)O) & 15) || (((uintptr_t)Gp) & 7)) return -1;
+  if (!(w == 32 && d == 3 && f == 16)) return -1;
+  using C = NCfg<3, 16, 32>;
+  switch (act) {
+    case PB_IDENTITY: return launch_rgb<C, PB_IDENTITY>(ctx, I, Wt, O, Gp, out, lr, mode, (int)batch);
+    case PB_RELU: return launch_rgb<C, PB_RELU>(ctx, I, Wt, O, Gp, out, lr, mode, (int)batch);
+    case PB_LEAKY_RELU: return launch_rgb<C, PB_LEAKY_RELU>(ctx, I, Wt, O, Gp, out, lr, mode, (int)batch);
+    case PB_SIGMOID: return launch_rgb<C, PB_SIGMOID>(ctx, I, Wt, O, Gp, out, lr, mode, (int)batch);
+    default: return -1;
+  }
 }
 
 }  // namespace pb

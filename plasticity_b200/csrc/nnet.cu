@@ -198,6 +198,24 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
       // dE/d(conv output) from the pooled gradient and the stored convolution output inside
       // its producers (and writes it out once, for the weight gradient that follows).
       const int cl = l - 2;
+      if (cl == 1 && net->alias_input) {
+        // First convolution of the network: BatchTrain hands nobody dE/dInput (nnet.h:617-622
+        // passes a null input_gradients), so only the weight gradient is left to do, and its
+        // kernel forms dE/d(conv output) from the pooled gradient by itself.
+        float *Wc = net->weights + net->w_off[cl];
+        const int m = in_place ? PB_NEW_WEIGHTS : first_chunk ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
+        float *out = in_place ? Wc : net->deltas + net->w_off[cl];
+        const float *in = layer_in[cl] ? layer_in[cl] : net->outputs[cl - 1];
+        const int wrc = conv_act_pool_weight_update_mma(net->ctx, &net->layers[cl],
+                                                        net->layers[l - 1].activation, L, in, Wc,
+                                                        net->outputs[cl], g, out, net->lr, m, batch);
+        if (wrc > 0) return 1;
+        if (wrc == 0) {
+          mark(net, layer_tag(net, cl) + ":activation+pool backward+weight_update");
+          if (!in_place && fire_delta_hook(net, cl, last_chunk)) return 1;
+          break;  // layer 0 is the aliased input
+        }
+      }
       if (!net->grad_c) {
         if (cudaMalloc((void **)&net->grad_c, sizeof(float) * (size_t)(net->max_io * net->max_batch)) !=
             cudaSuccess) {
