@@ -400,13 +400,16 @@ conv_wt_kernel(const float *__restrict__ In, const float *__restrict__ Wt, float
 #pragma unroll
       for (int c0 = 0; c0 < LD; c0 += 8) tmem_ld8(taddr + c0, &v[c0]);
       tmem_ld_wait();
+      // only what reaches an fx = 0 lane is exchanged: pair sums for columns 0 .. W+1 (the
+      // fx = 2 lane's feed the second round at +2), then W columns per round
+      static_assert(C::W + 3 < LD, "columns of the first round");
 #pragma unroll
-      for (int j = 0; j + 1 < LD; ++j) {
+      for (int j = 0; j < C::W + 2; ++j) {
         const float t = __shfl_down_sync(0xffffffffu, v[j + 1], 1);
         v[j] += adds ? t : 0.0f;
       }
 #pragma unroll
-      for (int j = 0; j + 2 < LD; ++j) {
+      for (int j = 0; j < C::W; ++j) {
         const float t = __shfl_down_sync(0xffffffffu, v[j + 2], 2);
         v[j] += adds ? t : 0.0f;
       }

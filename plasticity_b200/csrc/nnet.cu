@@ -264,8 +264,13 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
     }
     const float *in = layer_in[l] ? layer_in[l] : net->outputs[l - 1];
     float *W = net->nw[l] ? net->weights + net->w_off[l] : nullptr;
-    if (pb_layer_input_delta(net->ctx, L, in, W, g, ng, batch)) return 1;
-    mark(net, layer_tag(net, l) + ":input_delta");
+    // the layer behind the aliased input: nobody reads its input gradient (BatchTrain has no
+    // input_gradients parameter, nnet.h:617-622)
+    const bool unobserved = l == 1 && net->alias_input;
+    if (!unobserved) {
+      if (pb_layer_input_delta(net->ctx, L, in, W, g, ng, batch)) return 1;
+      mark(net, layer_tag(net, l) + ":input_delta");
+    }
     if (net->nw[l] > 0) {
       // in_place: W <- W - lr * sum_b grad_b directly (the layer's input_delta, the only
       // later reader of W in this step, is already queued ahead on the in-order stream)
