@@ -21,9 +21,11 @@
 // ONE accumulator and the MMAs run at the tensor rate (measured with the same operand shapes
 // in tools/umma_wgrad_probe.cu).  The fx sum crosses accumulator rows (= tensor-memory
 // lanes): the five rows of an output channel sit in ADJACENT lanes of one warp (six channels
-// per 32-lane quadrant, two lanes idle), so the epilogue adds them with three rounds of
-// lane-relative shuffles on registers read at fixed column offsets +1, +2, +4 - no staging
-// buffer, no dynamic register index - and the fx = 0 lane ends up with a whole image row.
+// per 32-lane quadrant, two lanes idle) and share the channel's image row - lane fl takes the
+// outputs x = fl (mod 5).  For one accumulator column the five lanes then need five different
+// rows: ONE indexed shuffle per column, every lane receiving a term of one of its outputs (no
+// staging buffer, no dynamic register index; tcgen05.ld cannot read at a lane offset -
+// tools/tmem_ld_probe.cu - so the exchange has to be a shuffle).
 //
 // Input gradient = the same kernel on G with flipped / channel-transposed filters and no
 // bias (with pad == filter/2 the reference's centre guard, convolution_layer.cc:209, is the
@@ -386,35 +388,40 @@ conv_wt_kernel(const float *__restrict__ In, const float *__restrict__ Wt, float
   } else {
     // ---- epilogue: TMEM -> registers -> shuffle sum over fx -> global -----------------------
     const int quad = warp & 3, sub = warp >> 2;
-    const int g = lane / C::F, fx = lane - g * C::F, oc = quad * kPerQuad + g;
-    const bool owner = fx == 0 && g < kPerQuad && oc < C::OC;   // ends up with the whole row
-    const bool adds = fx != C::F - 1;                           // fx = 4 keeps its raw values
+    const int g = lane / C::F, fl = lane - g * C::F, oc = quad * kPerQuad + g;
+    const bool live = g < kPerQuad && oc < C::OC;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const float bias = owner ? bias_s[oc] : 0.0f;
-    // columns loaded per row: W + 4 matter, the rest (the next row's, or past the tile) only
-    // feeds sums that are never stored
-    constexpr int LD = ((C::W + C::F - 1 + 7) / 8) * 8;
+    const float bias = live ? bias_s[oc] : 0.0f;
+    // The five lanes of a channel SHARE its image row: lane fl ends up with the outputs
+    // x = fl, fl + 5, fl + 10, ... (slot s: x = fl + 5s).  Column c = 5q + r of the accumulator
+    // row fx belongs to output x = c - fx; for a fixed c the five lanes fetch it from the five
+    // DIFFERENT rows fx = (r - fl) mod 5 - one indexed shuffle per column in which every lane
+    // receives a value it needs (the fx-tree of the first version moved 50 registers per row for
+    // one receiving lane in five; the shuffle pipe was the kernel's bound) - and add it to slot q
+    // (r >= fl) or q - 1.
+    constexpr int NC = C::W + C::F - 1;            // accumulator columns of one image row
+    constexpr int LD = ((NC + 7) / 8) * 8;
+    constexpr int NS = (NC + C::F - 1) / C::F;     // slots per lane
     static_assert(2 * C::N + LD - C::P <= C::TMEM_COLS, "row window stays inside the allocation");
-    // one image row of the tile: v[x] = sum_fx D[(oc,fx)][row*P + x + fx] in the owner lane
-    auto row_sum = [&](uint32_t taddr, float (&v)[LD]) {
+    int src[C::F];
+#pragma unroll
+    for (int r = 0; r < C::F; ++r) src[r] = g < kPerQuad ? g * C::F + (r - fl + C::F) % C::F : lane;
+    const int pair_src = g < kPerQuad ? (fl < C::F - 1 ? lane + 1 : lane - (C::F - 1)) : lane;
+    auto row_fold = [&](uint32_t taddr, float (&acc)[NS]) {
+      float v[LD];
 #pragma unroll
       for (int c0 = 0; c0 < LD; c0 += 8) tmem_ld8(taddr + c0, &v[c0]);
       tmem_ld_wait();
-      // only what reaches an fx = 0 lane is exchanged: pair sums for columns 0 .. W+1 (the
-      // fx = 2 lane's feed the second round at +2), then W columns per round
-      static_assert(C::W + 3 < LD, "columns of the first round");
 #pragma unroll
-      for (int j = 0; j < C::W + 2; ++j) {
-        const float t = __shfl_down_sync(0xffffffffu, v[j + 1], 1);
-        v[j] += adds ? t : 0.0f;
+      for (int q = 0; q < NS; ++q) acc[q] = bias;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        constexpr int F = C::F;
+        const int q = c / F, r = c % F;
+        const float t = __shfl_sync(0xffffffffu, v[c], src[r]);
+        if (r >= fl) acc[q] += t;
+        else if (q > 0) acc[q - 1] += t;
       }
-#pragma unroll
-      for (int j = 0; j < C::W; ++j) {
-        const float t = __shfl_down_sync(0xffffffffu, v[j + 2], 2);
-        v[j] += adds ? t : 0.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < C::W; ++j) v[j] = (v[j] + __shfl_down_sync(0xffffffffu, v[j + 4], 4)) + bias;
     };
     int tc = 0;
     for (int item = blockIdx.x; item < batch; item += gridDim.x) {
@@ -430,33 +437,33 @@ conv_wt_kernel(const float *__restrict__ In, const float *__restrict__ Wt, float
 #pragma unroll 1
         for (int rp = sub; rp < C::TR / 2; rp += 2) {   // row pairs of the tile, alternating warps
           const int y = tile * C::TR + 2 * rp;
-          float o0[C::W];
-          {
-            float v[LD];
-            row_sum(d_tile + (uint32_t)((2 * rp) * C::P), v);
+          float o0[NS], o1[NS];
+          row_fold(d_tile + (uint32_t)((2 * rp) * C::P), o0);
+          row_fold(d_tile + (uint32_t)((2 * rp + 1) * C::P), o1);
+          float *dst = Out + (((int64_t)item * C::OC + oc) * C::H + y) * C::W + fl;
 #pragma unroll
-            for (int j = 0; j < C::W; ++j) o0[j] = v[j];
-          }
-          float v[LD];
-          row_sum(d_tile + (uint32_t)((2 * rp + 1) * C::P), v);
-          if (owner) {
-            float *dst = Out + (((int64_t)item * C::OC + oc) * C::H + y) * C::W;
-#pragma unroll
-            for (int j = 0; j < C::W; j += 4) {
-              *reinterpret_cast<float4 *>(dst + j) = make_float4(o0[j], o0[j + 1], o0[j + 2], o0[j + 3]);
-              *reinterpret_cast<float4 *>(dst + C::W + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int q = 0; q < NS; ++q) {
+            if (live && fl + C::F * q < C::W) {
+              dst[C::F * q] = o0[q];
+              dst[C::W + C::F * q] = o1[q];
             }
-            if constexpr (!C::BWD && ACT >= 0) {
-              float *dst2 = Out2 + (((int64_t)item * C::OC + oc) * (C::H / 2) + (y >> 1)) * (C::W / 2);
+          }
+          if constexpr (!C::BWD && ACT >= 0) {
+            // 2x2 pool: vertical maximum in the lane, the odd column's from the lane that owns
+            // it (x + 1: the next lane's slot q, or - from the last lane - the first lane's q + 1)
+            float m[NS], nb[NS];
 #pragma unroll
-              for (int j = 0; j < C::W; j += 8) {
-                float m[4];
+            for (int q = 0; q < NS; ++q) m[q] = fmaxf(o0[q], o1[q]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  m[q] = act_fwd<(ACT >= 0 ? ACT : 0)>(fmaxf(fmaxf(o0[j + 2 * q], o0[j + 2 * q + 1]),
-                                                             fmaxf(v[j + 2 * q], v[j + 2 * q + 1])));
-                *reinterpret_cast<float4 *>(dst2 + j / 2) = make_float4(m[0], m[1], m[2], m[3]);
-              }
+            for (int q = 0; q < NS; ++q) nb[q] = __shfl_sync(0xffffffffu, m[q], pair_src);
+            float *dst2 = Out2 + (((int64_t)item * C::OC + oc) * (C::H / 2) + (y >> 1)) * (C::W / 2);
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+              const int x = fl + C::F * q;
+              const float up = q + 1 < NS ? nb[q + 1] : 0.0f;
+              const float other = fl < C::F - 1 ? nb[q] : up;
+              if (live && x < C::W && !(x & 1))
+                dst2[x >> 1] = act_fwd<(ACT >= 0 ? ACT : 0)>(fmaxf(m[q], other));
             }
           }
         }
