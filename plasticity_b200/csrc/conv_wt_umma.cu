@@ -545,9 +545,10 @@ int conv_evaluate_wt(pb_context *ctx, const pb_layer_desc *l, const float *I, co
   if (!wt_shape(l, batch) || (((uintptr_t)O) & 15)) return -1;
   const int w = (int)l->width, d = (int)l->depth, f = (int)l->num_filters;
   // (the RGB layer's forward pass - K = 15, 80 accumulator rows to fold per 16 outputs, only 648
-  // MMA cycles per tile - is bound by the epilogue here: 93 us with the shuffle fold, 74 us with
-  // a quadrant-per-fx row order folded through a shared-memory tile, against conv_umma.cu's
-  // 50 us, which keeps it)
+  // MMA cycles per tile - is bound by the epilogue here: 93 us with the first shuffle fold, 74 us
+  // with a quadrant-per-fx row order folded through a shared-memory tile, 50 us (75 us with the
+  // fused activation + pool) with the one-shuffle-per-column fold, against conv_umma.cu's 43 us,
+  // which keeps it)
   if (w == 16 && d == 16 && f == 20) return launch_wt<TCfg<16, 20, 16, 4, false>>(ctx, I, W, O, batch);
   if (w == 8 && d == 20 && f == 20) return launch_wt<TCfg<20, 20, 8, 4, false>>(ctx, I, W, O, batch);
   return -1;
