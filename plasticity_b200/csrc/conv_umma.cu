@@ -543,7 +543,9 @@ bool umma_enabled() {
 int conv_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
                        float *O, int64_t batch) {
   {
-    const int rc = conv_evaluate_wt(ctx, l, I, W, O, batch);
+    int rc = conv_evaluate_wt(ctx, l, I, W, O, batch);
+    if (rc >= 0) return rc;
+    rc = conv_evaluate_rows(ctx, l, I, W, O, batch);
     if (rc >= 0) return rc;
   }
   if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;
@@ -572,7 +574,9 @@ int conv_act_pool_evaluate_umma(pb_context *ctx, const pb_layer_desc *l, int act
                                 const pb_layer_desc *pool, const float *I, const float *W,
                                 float *O, float *O2, int64_t batch) {
   {
-    const int rc = conv_act_pool_evaluate_wt(ctx, l, act, pool, I, W, O, O2, batch);
+    int rc = conv_act_pool_evaluate_wt(ctx, l, act, pool, I, W, O, O2, batch);
+    if (rc >= 0) return rc;
+    rc = conv_act_pool_evaluate_rows(ctx, l, act, pool, I, W, O, O2, batch);
     if (rc >= 0) return rc;
   }
   if (!umma_enabled() || l->stride != 1 || batch > (1 << 24)) return -1;

@@ -116,6 +116,15 @@ int conv_act_pool_input_delta_wt(pb_context *ctx, const pb_layer_desc *conv, int
                                  const pb_layer_desc *pool, const float *W, const float *O_conv,
                                  const float *Gp, float *G_out, float *dI, int64_t batch);
 
+// conv_rows_umma.cu: the forward pass of the network's first (RGB) layer with the image rows in
+// tensor memory and the fy taps summed over tiles in registers; tried first, -1 outside the
+// envelope.
+int conv_evaluate_rows(pb_context *ctx, const pb_layer_desc *l, const float *I, const float *W,
+                       float *O, int64_t batch);
+int conv_act_pool_evaluate_rows(pb_context *ctx, const pb_layer_desc *conv, int act,
+                                const pb_layer_desc *pool, const float *I, const float *W,
+                                float *O_conv, float *O_pool, int64_t batch);
+
 // conv_gemm_umma.cu: general implicit-GEMM tensor-core convolution (forward) for large
 // batched shapes, any filter / stride / padding; O2 != nullptr additionally receives
 // act(O), the output of a following ActivationLayer.  -1 outside the envelope.
