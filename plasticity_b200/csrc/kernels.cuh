@@ -73,6 +73,12 @@ int conv_weight_update_tiled(pb_context *ctx, const pb_layer_desc *l, const floa
 
 // conv_wgrad_mma.cu: 3xTF32 mma.sync weight gradient for the 5x5 stride-1 layers whose
 // channel counts fill an MMA tile; -1 outside the envelope.
+// conv_wgrad_rows_umma.cu: the same for the first layer of the CIFAR network on tcgen05 (bands
+// of image rows, the row offset as a free index of both operands); tried first.
+int conv_act_pool_weight_update_rows(pb_context *ctx, const pb_layer_desc *l, int act,
+                                     const pb_layer_desc *pool, const float *I, const float *Wt,
+                                     const float *O, const float *Gp, float *out, const float *lr,
+                                     int mode, int64_t batch);
 int conv_act_pool_weight_update_mma(pb_context *ctx, const pb_layer_desc *l, int act,
                                     const pb_layer_desc *pool, const float *I, const float *Wt,
                                     const float *O, const float *Gp, float *out, const float *lr,

@@ -206,9 +206,13 @@ static int backward_fused(pb_nnet *net, int64_t batch, float *g, float *ng, bool
         const int m = in_place ? PB_NEW_WEIGHTS : first_chunk ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
         float *out = in_place ? Wc : net->deltas + net->w_off[cl];
         const float *in = layer_in[cl] ? layer_in[cl] : net->outputs[cl - 1];
-        const int wrc = conv_act_pool_weight_update_mma(net->ctx, &net->layers[cl],
-                                                        net->layers[l - 1].activation, L, in, Wc,
-                                                        net->outputs[cl], g, out, net->lr, m, batch);
+        int wrc = conv_act_pool_weight_update_rows(net->ctx, &net->layers[cl],
+                                                   net->layers[l - 1].activation, L, in, Wc,
+                                                   net->outputs[cl], g, out, net->lr, m, batch);
+        if (wrc < 0)
+          wrc = conv_act_pool_weight_update_mma(net->ctx, &net->layers[cl],
+                                                net->layers[l - 1].activation, L, in, Wc,
+                                                net->outputs[cl], g, out, net->lr, m, batch);
         if (wrc > 0) return 1;
         if (wrc == 0) {
           mark(net, layer_tag(net, cl) + ":activation+pool backward+weight_update");

@@ -489,6 +489,8 @@ def test_train_loop_one_warp_kernel(ctx, name, monkeypatch):
     {"PB_CONV_WT": "0"},          # convolution forward / input gradient: conv_umma.cu kernels
     {"PB_WGRAD_UMMA": "0"},       # weight gradient: mma.sync kernels for all three layers
     {"PB_WGRAD_FORM": "0"},       # first convolution: separate pool/activation backward kernel
+    {"PB_WGRAD_ROWS": "0"},       # first convolution: mma.sync weight gradient (fused forming)
+    {"PB_CONV_ROWS": "0"},        # first convolution forward: conv_umma.cu
     {"PB_WGRAD_UMMA": "0", "PB_WGRAD_MMA": "0"},   # weight gradient: FFMA kernels
     {"PB_DISABLE_UMMA": "1"},     # no tensor-core kernel anywhere
     {"PB_DISABLE_FUSION": "1"},   # layer-by-layer plan
