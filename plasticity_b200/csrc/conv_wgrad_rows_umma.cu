@@ -74,7 +74,7 @@ struct WCfgR {
   static constexpr int NW = OC * K1;                // floats per partial
   static constexpr int DP = N + 1;                  // accumulator row pitch in shared memory
   static constexpr int PF = 4;                      // bands in flight per forming thread
-  static constexpr int RAW4 = (PF + 1) * G_THREADS * 2 + (PF + 1) * G_THREADS / 2;  // float4 units
+  static constexpr int RAW4 = (PF + 2) * G_THREADS * 2 + (PF + 2) * G_THREADS / 2;  // float4 units
   static constexpr size_t SMEM = sizeof(float) * (size_t)(2 * IMG + NB * B_STAGE + 4 * RAW4) + 8 * (2 * NSLOT + 2 * NB + 1) + 16;
   static_assert(ROWS + 1 <= 128 && N % 16 == 0 && A_COL0 + NSLOT * SLOT_COLS <= TMEM_COLS, "tile shape");
   static_assert(SP % 32 == 5 && PLANE % 32 == 8, "conflict-free pitches");
@@ -121,6 +121,15 @@ conv_wgrad_rows_kernel(const float *__restrict__ In, const float *__restrict__ O
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(d_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef PB_WROWS_PROF
+  long long pt_[4] = {0, 0, 0, 0};
+  const long long pt_start = clock64();
+#define PROF_T0 const long long pt0_ = clock64();
+#define PROF_ADD(i) pt_[i] += clock64() - pt0_;
+#else
+#define PROF_T0
+#define PROF_ADD(i)
+#endif
 
   // ---- one-time setup (runs ahead of the dependency wait of a chained launch) ------
   for (int i = tid; i < 2 * C::IMG; i += C::THREADS) img_s[i] = 0.0f;   // pads stay zero
@@ -186,7 +195,9 @@ conv_wgrad_rows_kernel(const float *__restrict__ In, const float *__restrict__ O
         float v[C::W];
 #pragma unroll
         for (int x = 0; x < C::W; ++x) v[x] = live ? row0[band * C::BR * C::SP + x] : fill;
+        { PROF_T0
         mbar_wait(&a_empty[slot], ph ^ 1);
+        PROF_ADD(0) }
         tc_fence_after();
         const uint32_t col = tmem_base + lane_base + (uint32_t)(C::A_COL0 + slot * C::SLOT_COLS);
 #pragma unroll
@@ -205,8 +216,13 @@ conv_wgrad_rows_kernel(const float *__restrict__ In, const float *__restrict__ O
         if (lane == 0) mbar_arrive(&a_full[slot]);
       }
       if (next < batch) store_sample(st ^ 1);   // its readers finished a sample ago
+      { PROF_T0
       asm volatile("bar.sync 1, %0;" ::"n"(C::A_THREADS) : "memory");
+      PROF_ADD(1) }
     }
+#ifdef PB_WROWS_PROF
+    if (blockIdx.x == 0 && tid == 0) printf("wrows A producer: total %lld | wait a_empty %lld, sample barrier %lld\n", clock64() - pt_start, pt_[0], pt_[1]);
+#endif
   } else if (warp == C::MMA_WARP) {
     // ---- MMA issuer ------------------------------------------------------------------
     const bool leader = elect_one();
@@ -219,8 +235,12 @@ conv_wgrad_rows_kernel(const float *__restrict__ In, const float *__restrict__ O
       for (int band = 0; band < C::BANDS; ++band, ++tc) {
         const int slot = tc % C::NSLOT, aph = (tc / C::NSLOT) & 1;
         const int bs = tc % C::NB, bph = (tc / C::NB) & 1;
+        { PROF_T0
         mbar_wait(&b_full[bs], bph);
+        PROF_ADD(0) }
+        { PROF_T0
         mbar_wait(&a_full[slot], aph);
+        PROF_ADD(1) }
         tc_fence_after();
         if (leader) {
           const uint32_t a_col = tmem_base + (uint32_t)(C::A_COL0 + slot * C::SLOT_COLS);
@@ -244,6 +264,9 @@ conv_wgrad_rows_kernel(const float *__restrict__ In, const float *__restrict__ O
     }
     if (leader) umma_commit(d_full);
     __syncwarp();
+#ifdef PB_WROWS_PROF
+    if (blockIdx.x == 0 && lane == 0) printf("wrows MMA warp: total %lld | wait b_full %lld, wait a_full %lld\n", clock64() - pt_start, pt_[0], pt_[1]);
+#endif
   } else {
     // ---- gradient formers -----------------------------------------------------------------
     // a thread owns two pool windows (2 rows x 4 columns) of one filter plane per band
@@ -254,30 +277,34 @@ conv_wgrad_rows_kernel(const float *__restrict__ In, const float *__restrict__ O
     const int at = xq * C::B_LBO + (n0 >> 3) * 32 + (n0 & 7) * 4;   // n0 is even: n0 + 1 is in the same core matrix
     // the thread's pieces of the next PF bands are in flight (cp.async into its own slots of a
     // small ring: no register cost, no barrier - a thread reads back only what it copied)
-    constexpr int PF = C::PF, RS = PF + 1;
+    constexpr int PF = C::PF, RS = PF + 2;
     float4 *r0 = raw_s + pt, *r1 = r0 + RS * C::G_THREADS;
     float2 *rg = reinterpret_cast<float2 *>(raw_s + 2 * RS * C::G_THREADS) + pt;
     const int n_mine = (int)blockIdx.x < batch ? (batch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int T = n_mine * C::BANDS;
+    // the copy stream walks (sample, band) with running pointers: no division per band
+    const int64_t o_item = (int64_t)gridDim.x * C::OC * C::H * C::W - (int64_t)C::BANDS * C::BR * C::W;
+    const int64_t g_item = (int64_t)gridDim.x * C::OC * (C::H / 2) * (C::W / 2) - (int64_t)C::BANDS * (C::BR / 2) * (C::W / 2);
+    const float *o_nxt = O + (((int64_t)blockIdx.x * C::OC + oc) * C::H + 2 * rp) * C::W + 4 * xq;
+    const float *g_nxt = Gp + (((int64_t)blockIdx.x * C::OC + oc) * (C::H / 2) + rp) * (C::W / 2) + 2 * xq;
+    int band_nxt = 0, rs_nxt = 0;
     auto issue = [&](int u) {
       if (u < T) {
-        const int item = blockIdx.x + (u / C::BANDS) * gridDim.x, band = u % C::BANDS, rs = u % RS;
-        const float *o = O + (((int64_t)item * C::OC + oc) * C::H + band * C::BR + 2 * rp) * C::W + 4 * xq;
-        const float *gp = Gp + (((int64_t)item * C::OC + oc) * (C::H / 2) + band * (C::BR / 2) + rp) * (C::W / 2) + 2 * xq;
-        __pipeline_memcpy_async(r0 + rs * C::G_THREADS, o, 16);
-        __pipeline_memcpy_async(r1 + rs * C::G_THREADS, o + C::W, 16);
-        __pipeline_memcpy_async(rg + rs * C::G_THREADS, gp, 8);
+        __pipeline_memcpy_async(r0 + rs_nxt * C::G_THREADS, o_nxt, 16);
+        __pipeline_memcpy_async(r1 + rs_nxt * C::G_THREADS, o_nxt + C::W, 16);
+        __pipeline_memcpy_async(rg + rs_nxt * C::G_THREADS, g_nxt, 8);
+        o_nxt += C::BR * C::W;
+        g_nxt += (C::BR / 2) * (C::W / 2);
+        if (++band_nxt == C::BANDS) { band_nxt = 0; o_nxt += o_item; g_nxt += g_item; }
+        if (++rs_nxt == RS) rs_nxt = 0;
       }
       __pipeline_commit();
     };
 #pragma unroll
     for (int u = 0; u < PF; ++u) issue(u);
     {
-#pragma unroll 1
-      for (int tc = 0; tc < T; ++tc) {
-        const int bs = tc % C::NB, ph = (tc / C::NB) & 1, rs = tc % RS;
-        issue(tc + PF);
-        __pipeline_wait_prior(PF);
+      // two bands per iteration: two independent dependency chains per thread
+      auto form = [&](int rs, float4 &h0, float4 &h1, float4 &l0, float4 &l1) {
         const float4 p0 = r0[rs * C::G_THREADS];
         const float4 p1 = r1[rs * C::G_THREADS];
         const float2 gg = rg[rs * C::G_THREADS];
@@ -296,19 +323,46 @@ conv_wgrad_rows_kernel(const float *__restrict__ In, const float *__restrict__ O
         d1.y = act_bwd<ACTV>(p1.y, a11 < m0 ? 0.0f : gg.x);
         d1.z = act_bwd<ACTV>(p1.z, a12 < m1 ? 0.0f : gg.y);
         d1.w = act_bwd<ACTV>(p1.w, a13 < m1 ? 0.0f : gg.y);
-        const float4 h0 = make_float4(tf32_trunc(d0.x), tf32_trunc(d0.y), tf32_trunc(d0.z), tf32_trunc(d0.w));
-        const float4 h1 = make_float4(tf32_trunc(d1.x), tf32_trunc(d1.y), tf32_trunc(d1.z), tf32_trunc(d1.w));
+        h0 = make_float4(tf32_trunc(d0.x), tf32_trunc(d0.y), tf32_trunc(d0.z), tf32_trunc(d0.w));
+        h1 = make_float4(tf32_trunc(d1.x), tf32_trunc(d1.y), tf32_trunc(d1.z), tf32_trunc(d1.w));
+        l0 = make_float4(d0.x - h0.x, d0.y - h0.y, d0.z - h0.z, d0.w - h0.w);
+        l1 = make_float4(d1.x - h1.x, d1.y - h1.y, d1.z - h1.z, d1.w - h1.w);
+      };
+      auto publish = [&](int tc, const float4 &h0, const float4 &h1, const float4 &l0, const float4 &l1) {
+        const int bs = tc % C::NB, ph = (tc / C::NB) & 1;
+        { PROF_T0
         mbar_wait(&b_empty[bs], ph ^ 1);
+        PROF_ADD(1) }
         float *hi = b_s + bs * C::B_STAGE + at, *lo = hi + C::B_SET;
         *reinterpret_cast<float4 *>(hi) = h0;
         *reinterpret_cast<float4 *>(hi + 4) = h1;
-        *reinterpret_cast<float4 *>(lo) = make_float4(d0.x - h0.x, d0.y - h0.y, d0.z - h0.z, d0.w - h0.w);
-        *reinterpret_cast<float4 *>(lo + 4) = make_float4(d1.x - h1.x, d1.y - h1.y, d1.z - h1.z, d1.w - h1.w);
+        *reinterpret_cast<float4 *>(lo) = l0;
+        *reinterpret_cast<float4 *>(lo + 4) = l1;
         fence_async_proxy();
         __syncwarp();
         if (lane == 0) mbar_arrive(&b_full[bs]);
+      };
+      static_assert(C::BANDS % 2 == 0 && PF % 2 == 0, "bands are formed in pairs");
+      static_assert(RS % 2 == 0, "a pair of bands never wraps inside the ring");
+      int rs = 0;
+#pragma unroll 1
+      for (int tc = 0; tc < T; tc += 2) {
+        issue(tc + PF);
+        issue(tc + PF + 1);
+        { PROF_T0
+        __pipeline_wait_prior(PF);
+        PROF_ADD(0) }
+        float4 ha0, ha1, la0, la1, hb0, hb1, lb0, lb1;
+        form(rs, ha0, ha1, la0, la1);
+        form(rs + 1, hb0, hb1, lb0, lb1);
+        rs = rs + 2 == RS ? 0 : rs + 2;
+        publish(tc, ha0, ha1, la0, la1);
+        publish(tc + 1, hb0, hb1, lb0, lb1);
       }
     }
+#ifdef PB_WROWS_PROF
+    if (blockIdx.x == 0 && pt == 0) printf("wrows former: total %lld | wait cp.async %lld, wait b_empty %lld\n", clock64() - pt_start, pt_[0], pt_[1]);
+#endif
   }
 
   // ---- epilogue: fold the row offsets, one partial per CTA ---------------------------------
