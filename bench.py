@@ -2,7 +2,7 @@
 """bench.py — CIFAR CNN training throughput of the B200 layer path.
 
 Metric (BASELINE.json): CIFAR CNN train samples/sec, beside the reference's
-host-CPU path, with the dominant kernel's fraction of the FP32 roofline.
+host-CPU path, with the dominant kernel's fraction of the 3xTF32 tensor roofline.
 
 Workload ("cifar_cnn_batch_train"): the 13-layer network of
 nnet/cifar_test.cc:293-350 (22 466 parameters), cross-entropy, lr 1e-4,
@@ -32,8 +32,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cifar_cnn_train_samples_per_sec"
 UNIT = "samples/s"
-# fwd + input-grad + weight-grad MACs of the CIFAR net, x2.
-TRAIN_FLOP_PER_SAMPLE = 23.52e6
+# fwd + input-grad + weight-grad MACs of the CIFAR net, x2 (23.52e6), minus the
+# input gradient of the first convolution (2 x 1.2288e6 MAC): BatchTrain has no reader for
+# dE/dInput (nnet.h:617-622 passes a null input_gradients) and the step does not compute it.
+TRAIN_FLOP_PER_SAMPLE = 23.52e6 - 2 * 1.2288e6
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4
 
 
@@ -525,12 +527,34 @@ def run_ours(args):
             # input-gradient, conv weight gradient), FP32 FFMA (dense layers), or none
             # (elementwise: HBM)
             k = r["kernel"]
-            wgrad = k in ("convolution_layer_1:weight_update", "convolution_layer_4:weight_update",
-                          "convolution_layer_7:weight_update")
-            tcgen05 = not umma_off and ("tcgen05" in k or (k.startswith("convolution") and
-                                        k.endswith(":input_delta")) or (wgrad and wgrad_umma))
-            mma_sync = wgrad and not wgrad_umma and not umma_off and os.environ.get("PB_WGRAD_MMA") != "0"
+            is_conv = k.startswith("convolution")
+            wgrad = is_conv and k.endswith("weight_update")
+            first_fused = k == "convolution_layer_1:activation+pool backward+weight_update"
+            wrows = first_fused and os.environ.get("PB_WGRAD_ROWS") != "0"
+            first_fwd = k.startswith("convolution_layer_1:evaluate") and \
+                os.environ.get("PB_CONV_ROWS") != "0"
+            tcgen05 = not umma_off and ("tcgen05" in k or (is_conv and k.endswith(":input_delta")) or
+                                        (wgrad and not first_fused and wgrad_umma) or wrows)
+            mma_sync = wgrad and not tcgen05 and not umma_off and os.environ.get("PB_WGRAD_MMA") != "0"
             tensor_peak = bf16_peak / 2 / 3
+            if wrows:
+                pipe = ("tcgen05.mma kind::tf32, bands of image rows in tensor memory, the gradient "
+                        "formed from the pooled gradient and staged K-major in shared memory "
+                        "(conv_wgrad_rows_umma.cu); the time includes the fixed-order partial reduce + "
+                        "SGD update kernel")
+            elif mma_sync:
+                pipe = ("mma.sync.m16n8k8 tf32 (warp-level; measured peak 278 TFLOP/s of tf32 MMA "
+                        "work = 92.7 fp32-equivalent, tools/mma_sync_probe.cu)")
+            elif wgrad:
+                pipe = ("tcgen05.mma kind::tf32, gradient operand in tensor memory, image operand "
+                        "K-major in shared memory (conv_wgrad_umma.cu); the time includes the "
+                        "fixed-order partial reduce + SGD update kernel")
+            elif first_fwd:
+                pipe = ("tcgen05.mma kind::tf32, image rows in tensor memory, fy taps summed over "
+                        "tiles in registers (conv_rows_umma.cu)")
+            else:
+                pipe = ("tcgen05.mma kind::tf32, filters in tensor memory, image operand K-major in "
+                        "shared memory, fx taps folded by lane shuffles (conv_wt_umma.cu)")
             if r["flop"] > 0 and not (tcgen05 or mma_sync):
                 out = {"bound": "fp32", "peak": tf.value, "unit": "TFLOP/s",
                        "peak_source": "FP32 FFMA micro-benchmark in this run (pb_measure_fp32_tflops; "
@@ -542,14 +566,7 @@ def run_ours(args):
                                        "fallback 1590") + " / 2 (TF32 runs at half the bf16 rate) / 3 "
                                        "(3xTF32: three MMAs per fp32 product); achieved counts "
                                        "algorithmic fp32 FLOPs",
-                       "pipe": "mma.sync.m16n8k8 tf32 (warp-level; measured peak 278 TFLOP/s of tf32 "
-                               "MMA work = 92.7 fp32-equivalent, tools/mma_sync_probe.cu)" if mma_sync
-                               else ("tcgen05.mma kind::tf32, gradient operand in tensor memory, image "
-                                     "operand K-major in shared memory (conv_wgrad_umma.cu); the time "
-                                     "includes the fixed-order partial reduce + SGD update kernel"
-                                     if wgrad else
-                                     "tcgen05.mma kind::tf32, operands from shared memory (N <= 48: "
-                                     "bounded by operand fetch, DESIGN.md 3.2)")}
+                       "pipe": pipe}
             else:
                 out = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
@@ -588,6 +605,9 @@ def run_ours(args):
                        "blocks": len(blocks), "block_ms_min": min(blocks), "block_ms_max": max(blocks),
                        "timed_seconds": sum(blocks) * 1e-3},
             "config": {"workload": "cifar_cnn_batch_train", "mode": "gradient_sum_minibatch",
+                       "input_gradients": "not requested (BatchTrain's 3-argument overload, "
+                                          "nnet.h:617-622): dE/dInput of the first convolution has "
+                                          "no reader and is not computed",
                        "batch_per_gpu": B, "global_batch": B * world, "lr": 1e-4,
                        "loss": "cross_entropy",
                        "network": "nnet/cifar_test.cc:293-350 (13 layers, 22466 params)",

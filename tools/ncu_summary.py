@@ -83,6 +83,8 @@ def main():
         FW, BW = "evaluate+activation+pool (tcgen05)", "input_delta+activation+pool backward (tcgen05)"
         label_of = [
             (r"conv_wgrad_mma_rgb_kernel", "convolution_layer_1:weight_update"),
+            (r"conv_wgrad_rows_kernel", "convolution_layer_1:activation+pool backward+weight_update"),
+            (r"conv_rows_kernel", "convolution_layer_1:" + FW),
             (r"conv_wgrad_umma_kernel<unnamed>::GCfg<16, 20, 16,", "convolution_layer_4:weight_update"),
             (r"conv_wgrad_umma_kernel<unnamed>::GCfg<20, 20, 8,", "convolution_layer_7:weight_update"),
             (r"UCfg<3, 16, 32, 32, 5, 0, 0>, 2>", "convolution_layer_1:" + FW),
