@@ -63,6 +63,12 @@ def main(argv=None):
         elif d.kind == L.PB_DENSE:
             macs += l.num_inputs * l.num_outputs
     flop_img = 3 * 2.0 * macs
+    # the input gradient of the first weighted layer has no reader (TrainBatch returns no
+    # dE/dInput) and is not computed: not counted either
+    first = next(l for l in layers if l.desc.kind in (L.PB_CONVOLUTION, L.PB_DENSE))
+    d = first.desc
+    flop_img -= 2.0 * (first.num_outputs * d.filter_width * d.filter_height * d.filter_depth
+                       if d.kind == L.PB_CONVOLUTION else first.num_inputs * first.num_outputs)
     prof = bench.step_profile(L, net, C.c_void_p(x.data_ptr()), C.c_void_p(e.data_ptr()), B, reps=1)
     rows = sorted(({"k": k, "ms": round(v, 3)} for k, v in prof), key=lambda r: -r["ms"])
     peaks = {}
