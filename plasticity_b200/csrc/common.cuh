@@ -17,9 +17,24 @@ struct pb_context {
   // Staging for double<->float conversion at the host boundary.
   double *stage = nullptr;
   size_t stage_elems = 0;
-  // Partial-sum workspace for batched weight gradients.
+  // Partial-sum workspace for batched weight gradients: `workspace` is the region the last
+  // ensure_workspace() call handed out, inside one allocation (ws_base, ws_cap floats).
+  // Outside a forked step every call gets the start of the allocation; inside one
+  // (fork_mode) the regions are carved one behind the other, because a weight-gradient
+  // kernel's partials are still being read by its reduce kernel on the side stream while
+  // the next weight-gradient kernel writes its own.
   float *workspace = nullptr;
   size_t workspace_elems = 0;
+  float *ws_base = nullptr;
+  size_t ws_cap = 0, ws_off = 0;
+  // Fork/join inside a fused training step (pb::launch_forked / pb::join_forked): the small
+  // fixed-order reduce + update kernels behind the weight-gradient kernels run on `fork_stream`
+  // beside the next layer's kernels instead of in front of them.
+  bool fork_mode = false;
+  cudaStream_t fork_stream = nullptr;
+  static constexpr int kMaxForks = 16;
+  cudaEvent_t fork_ev[kMaxForks] = {nullptr}, join_ev[kMaxForks] = {nullptr};
+  int forks = 0;
   // Re-tiled convolution weights of the implicit-GEMM kernel (conv_gemm_umma.cu).
   float *aux = nullptr;
   size_t aux_elems = 0;
@@ -139,6 +154,36 @@ inline cudaError_t launch_chained(pb_context *ctx, void (*kern)(KArgs...), dim3 
   }
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
+
+// A kernel that nothing on the compute stream needs before the end of the step (join_forked):
+// inside a forked step it is queued on ctx->fork_stream behind everything queued on ctx->stream
+// so far - during a stream capture this becomes a branch of the step graph - otherwise it is a
+// chained launch on the compute stream like any other.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_forked(pb_context *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block,
+                                 size_t smem, Args... args) {
+  if (!ctx->fork_mode || ctx->forks >= pb_context::kMaxForks)
+    return launch_chained(ctx, kern, grid, block, smem, args...);
+  const int i = ctx->forks;
+  cudaError_t e = cudaSuccess;
+  if (!ctx->fork_stream) e = cudaStreamCreateWithFlags(&ctx->fork_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess && !ctx->fork_ev[i]) e = cudaEventCreateWithFlags(&ctx->fork_ev[i], cudaEventDisableTiming);
+  if (e == cudaSuccess && !ctx->join_ev[i]) e = cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->fork_ev[i], ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->fork_stream, ctx->fork_ev[i], 0);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->fork_stream;
+  e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->join_ev[i], ctx->fork_stream);
+  ctx->forks = i + 1;
+  return e;
+}
+// the compute stream waits for every forked kernel since the last join
+int join_forked(pb_context *ctx);
 
 }  // namespace pb
 

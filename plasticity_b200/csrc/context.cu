@@ -28,16 +28,32 @@ int ensure_stage(pb_context *ctx, size_t elems) {
 }
 
 int ensure_workspace(pb_context *ctx, size_t elems) {
-  if (ctx->workspace_elems >= elems) return 0;
-  // The old workspace may still be in use by queued kernels.
-  PB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (ctx->workspace) PB_CUDA(cudaFree(ctx->workspace));
-  ctx->workspace = nullptr;
-  ctx->workspace_elems = 0;
-  size_t want = std::max<size_t>(elems, 1 << 20);
-  PB_CUDA(cudaMalloc(&ctx->workspace, want * sizeof(float)));
-  ctx->workspace_elems = want;
-  ctx->alloc_generation++;
+  const size_t off = ctx->fork_mode ? ctx->ws_off : 0;
+  const size_t need = off + elems;
+  if (ctx->ws_cap < need) {
+    // The old allocation may still be in use by queued kernels (on either stream of a
+    // forked step: only its eager runs grow the workspace, a captured one finds it sized).
+    // (this context's streams only: another in-process rank's exchange kernel may be waiting
+    // on the device for the very step that is being queued here)
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->fork_stream) PB_CUDA(cudaStreamSynchronize(ctx->fork_stream));
+    if (ctx->ws_base) PB_CUDA(cudaFree(ctx->ws_base));
+    ctx->ws_base = nullptr;
+    ctx->ws_cap = 0;
+    size_t want = std::max<size_t>(need, 1 << 20);
+    PB_CUDA(cudaMalloc(&ctx->ws_base, want * sizeof(float)));
+    ctx->ws_cap = want;
+    ctx->alloc_generation++;
+  }
+  ctx->workspace = ctx->ws_base + off;
+  ctx->workspace_elems = ctx->ws_cap - off;
+  if (ctx->fork_mode) ctx->ws_off = (need + 63) & ~(size_t)63;   // 256-byte aligned regions
+  return 0;
+}
+
+int join_forked(pb_context *ctx) {
+  for (int i = 0; i < ctx->forks; ++i) PB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
+  ctx->forks = 0;
   return 0;
 }
 
@@ -132,7 +148,15 @@ int pb_context_destroy(pb_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->stage) cudaFree(ctx->stage);
-  if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->fork_stream) {
+    cudaStreamSynchronize(ctx->fork_stream);
+    cudaStreamDestroy(ctx->fork_stream);
+  }
+  for (int i = 0; i < pb_context::kMaxForks; ++i) {
+    if (ctx->fork_ev[i]) cudaEventDestroy(ctx->fork_ev[i]);
+    if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+  }
+  if (ctx->ws_base) cudaFree(ctx->ws_base);
   if (ctx->aux) cudaFree(ctx->aux);
   if (ctx->fault) cudaFreeHost(ctx->fault);
   cudaStreamDestroy(ctx->stream);

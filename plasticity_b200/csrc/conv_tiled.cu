@@ -406,7 +406,7 @@ wgrad_reduce_kernel(const float *__restrict__ partial, int n_partial, int nw, co
 
 int reduce_partials_update(pb_context *ctx, const float *partial, int n_partial, int nw,
                            const float *Wt, float *out, const float *lr, int mode) {
-  PB_CUDA(launch_chained(ctx, wgrad_reduce_kernel, dim3(pb_div_up(nw, 32)), dim3(256), 0, partial,
+  PB_CUDA(launch_forked(ctx, wgrad_reduce_kernel, dim3(pb_div_up(nw, 32)), dim3(256), 0, partial,
                          n_partial, nw, Wt, out, lr, mode));
   PB_LAUNCHED(ctx);
   return 0;

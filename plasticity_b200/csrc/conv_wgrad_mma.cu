@@ -310,7 +310,7 @@ int launch(pb_context *ctx, const float *I, const float *Wt, const float *G, flo
   PB_CUDA(launch_chained(ctx, kern, dim3(grid), dim3(kThreads), C::SMEM, I, G, ctx->workspace,
                          batch, spc));
   PB_LAUNCHED(ctx);
-  PB_CUDA(launch_chained(ctx, wgrad_mma_reduce_kernel<C>, dim3(pb_div_up(C::ROW, 32)), dim3(256), 0,
+  PB_CUDA(launch_forked(ctx, wgrad_mma_reduce_kernel<C>, dim3(pb_div_up(C::ROW, 32)), dim3(256), 0,
                          ctx->workspace, grid, Wt, out, lr, mode));
   PB_LAUNCHED(ctx);
   return 0;
@@ -609,7 +609,7 @@ int launch_rgb(pb_context *ctx, const float *I, const float *Wt, const float *G,
                          dim3(C::THREADS + (ACT >= 0 ? 32 * kFormWarps : 32)), C::SMEM, I, G, Gp,
                          ctx->workspace, batch, spc));
   PB_LAUNCHED(ctx);
-  PB_CUDA(launch_chained(ctx, wgrad_mma_rgb_reduce_kernel<C>, dim3(pb_div_up(C::ROW, 32)), dim3(256),
+  PB_CUDA(launch_forked(ctx, wgrad_mma_rgb_reduce_kernel<C>, dim3(pb_div_up(C::ROW, 32)), dim3(256),
                          0, ctx->workspace, grid, Wt, out, lr, mode));
   PB_LAUNCHED(ctx);
   return 0;

@@ -461,7 +461,7 @@ int launch(pb_context *ctx, const float *I, const float *Wt, const float *G, flo
   PB_CUDA(launch_chained(ctx, kern, dim3(grid), dim3(C::THREADS), C::SMEM, I, G, ctx->workspace, batch));
   PB_LAUNCHED(ctx);
   constexpr int SLOTS = C::F * C::IC * 128 + C::OC;
-  PB_CUDA(launch_chained(ctx, wgrad_umma_reduce_kernel<C>, dim3(pb_div_up(SLOTS, 32)), dim3(256), 0,
+  PB_CUDA(launch_forked(ctx, wgrad_umma_reduce_kernel<C>, dim3(pb_div_up(SLOTS, 32)), dim3(256), 0,
                          ctx->workspace, grid, Wt, out, lr, mode));
   PB_LAUNCHED(ctx);
   return 0;

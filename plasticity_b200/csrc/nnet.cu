@@ -754,11 +754,30 @@ static int batch_pass(pb_nnet *net, const float *d_ins, const float *d_expected,
     const char *e = getenv("PB_STEP_CHAIN");
     return !(e && e[0] == '0');
   }();
+  // Forked step (common.cuh launch_forked): the fixed-order reduce + update kernels behind the
+  // weight-gradient kernels (4-7 us each, four per step) run on a second stream beside the
+  // next layer's kernels and are joined at the end of the pass - a branch of the step graph.
+  // Nothing on the compute stream reads what they write before that: a layer's input gradient
+  // (the only other reader of its weights) is queued ahead of its weight gradient, and the
+  // delta buffer is read only behind the pass.  Not with a per-layer delta hook (the large
+  // data-parallel exchange starts a layer's exchange right behind its reduce).
+  // PB_STEP_FORK=0 turns it off.
+  static const bool fork_on = [] {
+    const char *e = getenv("PB_STEP_FORK");
+    return !(e && e[0] == '0');
+  }();
   (void)in_place;
-  net->ctx->chain = (chain_on && net->fuse && !net->profiling) ? 1 : 0;
-  net->ctx->chain_last = net->ctx->chain != 0;
-  const int rc = batch_pass_body(net, d_ins, d_expected, batch, in_place);
-  net->ctx->chain = 0;
+  pb_context *ctx = net->ctx;
+  ctx->chain = (chain_on && net->fuse && !net->profiling) ? 1 : 0;
+  ctx->chain_last = ctx->chain != 0;
+  // small networks only: the partial-sum regions of a forked pass lie one behind the other
+  ctx->fork_mode = fork_on && ctx->chain != 0 && !net->delta_hook && net->total_w <= (1 << 20);
+  ctx->ws_off = 0;
+  ctx->forks = 0;
+  int rc = batch_pass_body(net, d_ins, d_expected, batch, in_place);
+  if (pb::join_forked(ctx)) rc = 1;
+  ctx->fork_mode = false;
+  ctx->chain = 0;
   return rc;
 }
 

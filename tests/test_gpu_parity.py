@@ -496,6 +496,7 @@ def test_train_loop_one_warp_kernel(ctx, name, monkeypatch):
     {"PB_DISABLE_FUSION": "1"},   # layer-by-layer plan
     {"PB_STEP_GRAPHS": "0"},      # eager steps
     {"PB_STEP_CHAIN": "0"},       # no programmatic dependent launches
+    {"PB_STEP_FORK": "0"},        # reduce + update kernels on the compute stream
     {"PB_TRAIN_SMALL": "0"},      # per-sample loop as a replayed graph
 ], ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
 def test_library_switches(switches):
