@@ -31,6 +31,9 @@ struct pb_context {
   // fixed-order reduce + update kernels behind the weight-gradient kernels run on `fork_stream`
   // beside the next layer's kernels instead of in front of them.
   bool fork_mode = false;
+  // the caller of the next weight-gradient kernel guarantees that its operands stay untouched
+  // until the join (dedicated gradient buffer): the kernel itself may be forked, not only its reduce
+  bool fork_operands_stable = false;
   cudaStream_t fork_stream = nullptr;
   static constexpr int kMaxForks = 16;
   cudaEvent_t fork_ev[kMaxForks] = {nullptr}, join_ev[kMaxForks] = {nullptr};

@@ -245,8 +245,12 @@ int dense_weight_update_skinny(pb_context *ctx, const pb_layer_desc *l, const fl
   splits = (int)((batch + per_split - 1) / per_split);
   if (ensure_workspace(ctx, (size_t)splits * nw)) return 1;
   dim3 grid(col_tiles, splits);
-  PB_CUDA(launch_chained(ctx, dense_wgrad_skinny_kernel<16>, grid, dim3(256), 0, X, G,
-                         ctx->workspace, (int)in, (int)nout, batch, per_split));
+  if (ctx->fork_operands_stable)
+    PB_CUDA(launch_forked(ctx, dense_wgrad_skinny_kernel<16>, grid, dim3(256), 0, X, G,
+                          ctx->workspace, (int)in, (int)nout, batch, per_split));
+  else
+    PB_CUDA(launch_chained(ctx, dense_wgrad_skinny_kernel<16>, grid, dim3(256), 0, X, G,
+                           ctx->workspace, (int)in, (int)nout, batch, per_split));
   PB_LAUNCHED(ctx);
   return reduce_partials_update(ctx, ctx->workspace, splits, (int)nw, W, out, lr, mode);
 }

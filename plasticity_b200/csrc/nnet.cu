@@ -30,6 +30,8 @@ struct pb_nnet {
   std::vector<float *> outputs;
   float *grad_a = nullptr, *grad_b = nullptr;
   float *grad_c = nullptr;  // dE/d(convolution output) of a fused block (allocated on first use)
+  float *grad_z = nullptr;  // dE/d(dense output) of the fused head: its own buffer, so that the
+                            // dense weight gradient can run beside the next layer's backward
   float *lr = nullptr;
   float *err = nullptr;  // n_out loss components
   // strict per-sample SGD loop (pb_nnet_train_loop)
@@ -566,6 +568,7 @@ int pb_nnet_destroy(pb_nnet *net) {
   cudaFree(net->weights); cudaFree(net->deltas);
   cudaFree(net->grad_a); cudaFree(net->grad_b);
   if (net->grad_c) cudaFree(net->grad_c);
+  if (net->grad_z) cudaFree(net->grad_z);
   cudaFree(net->lr); cudaFree(net->err);
   cudaFree(net->stage_in); cudaFree(net->stage_exp); cudaFree(net->cursor);
   for (float *p : net->outputs) cudaFree(p);
@@ -804,18 +807,29 @@ static int batch_pass_body(pb_nnet *net, const float *d_ins, const float *d_expe
         // dE/dX to `g` — then the dense weight gradient, then the loop below.
         const float *X = layer_in[h];
         float *W = net->weights + net->w_off[h];
+        if (!net->grad_z) {
+          if (cudaMalloc((void **)&net->grad_z, sizeof(float) * (size_t)(net->no[h] * net->max_batch)) !=
+              cudaSuccess) {
+            cudaGetLastError();
+            net->grad_z = nullptr;
+          }
+        }
+        float *gz = net->grad_z ? net->grad_z : ng;
         const int rc = pb::head_forward_backward(
             ctx, &net->layers[h], net->layers[h + 1].activation, net->layers[h + 2].n, net->loss,
             X, W, d_expected + b0 * nout, net->outputs[h], net->outputs[h + 1],
-            net->outputs[h + 2], ng, g, nb);
+            net->outputs[h + 2], gz, g, nb);
         if (rc > 0) return 1;
         if (rc == 0) {
           pb::mark(net, pb::layer_tag(net, h) + ".." + pb::layer_tag(net, n - 1) +
                             ":evaluate+error_gradients+input_delta (head)");
           const int m = in_place ? PB_NEW_WEIGHTS : b0 == 0 ? PB_WEIGHT_DELTAS : PB_ACCUMULATE;
-          if (pb_layer_weight_update(ctx, &net->layers[h], X, W, ng,
-                                     in_place ? W : net->deltas + net->w_off[h], net->lr, m, nb))
-            return 1;
+          // X (a layer output) and gz (its own buffer) stay untouched until the end of the pass
+          ctx->fork_operands_stable = gz != ng;
+          const int wrc = pb_layer_weight_update(ctx, &net->layers[h], X, W, gz,
+                                                 in_place ? W : net->deltas + net->w_off[h], net->lr, m, nb);
+          ctx->fork_operands_stable = false;
+          if (wrc) return 1;
           pb::mark(net, pb::layer_tag(net, h) + ":weight_update");
           if (!in_place && pb::fire_delta_hook(net, h, b0 + net->max_batch >= batch)) return 1;
           top = h - 1;
@@ -838,6 +852,9 @@ static int batch_pass_body(pb_nnet *net, const float *d_ins, const float *d_expe
       if (pb::backward_fused(net, nb, g, ng, b0 == 0, layer_in, fused_fwd, top, in_place,
                              b0 + net->max_batch >= batch))
         return 1;
+      // the next chunk overwrites the layer outputs and gradient buffers the forked kernels read
+      if (pb::join_forked(ctx)) return 1;
+      ctx->ws_off = 0;
       continue;
     }
     if (pb::forward(net, in, nb)) return 1;
