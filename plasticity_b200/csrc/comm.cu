@@ -8,8 +8,8 @@
 // For small networks (the CIFAR net has 22 466 weights = 90 KB) the all-reduce is
 // pure latency, so the exchange and the weight update are ONE kernel over NVLink
 // peer memory behind the gradient pass (p2p_inbox_kernel): every rank pushes its delta
-// buffer into an inbox slot on every peer with remote stores, publishes a flag, waits
-// for the peers' flags and adds the contributions in rank order (bit-identical
+// buffer as (value, step tag) pairs into an inbox slot on every peer with 8-byte remote stores,
+// waits for the tags of the peers' pairs and adds the contributions in rank order (bit-identical
 // weights on all ranks) straight into W.  Inboxes are double-buffered by step
 // parity; peer memory is mapped with CUDA IPC handles exchanged through NCCL at
 // the first step.  Large delta buffers (the 4096-wide MLP) exchange layer by layer,
@@ -26,7 +26,7 @@
 
 constexpr int kMaxP2pRanks = 8;
 constexpr int64_t kMaxP2pFloats = 1 << 20;   // above this the exchange is bandwidth-bound: NCCL
-constexpr int kXCtas = 16;                   // CTAs of the small exchange kernel (one flag set each)
+constexpr int kXCtas = 32;                   // CTAs of the small exchange kernel (one step counter each)
 constexpr size_t kP2pHeader = 2048;          // bytes reserved for the flag words [2][kXCtas][ranks]
 constexpr int kMaxBuckets = 256;             // layers of a network (one exchange bucket each)
 // flag block of the large exchange, uint32 words:
@@ -137,16 +137,31 @@ __device__ __forceinline__ bool spin_until(volatile uint32_t *word, uint32_t epo
 }
 
 // The exchange step of a small network as ONE kernel, launched chained right behind the
-// gradient pass on the compute stream.  kXCtas CTAs; CTA c owns slice c of the flat buffer:
-//   push   its slice of this rank's deltas into slot [step parity][rank] of EVERY rank's
-//          inbox (remote stores over NVLink, posted);
-//   flag   one word per (parity, CTA, source rank) on every rank, then wait for the R words
-//          of this CTA on this rank - the only latency-bound point of the step;
+// gradient pass on the compute stream.  Every value travels with its own flag: an inbox slot
+// holds (value, step tag) pairs, written with ONE 8-byte remote store and read with one 8-byte
+// load, so the receiver needs no fence and no separate flag round trip - it spins on the tag of
+// the element it wants (the LL protocol of NCCL's small-message paths).  A first version pushed
+// plain floats, fenced at system scope, published a flag word and fenced again: the two
+// fences cost 20 us per step, eight times the data movement.  kXCtas CTAs; CTA c owns slice c
+// of the flat buffer:
+//   push   (delta, tag) of its slice into slot [step parity][rank] of EVERY rank's inbox
+//          (remote stores over NVLink, posted);
+//   wait   until the tags of its slice from every rank are the step's: one NVLink latency;
 //   apply  W[slice] += contributions in rank order, read from the local inbox: every rank
 //          forms the identical sum, so the weights stay bit-identical with no second barrier
-//          and no all-gather.  A rank cannot run two steps ahead of a peer (its next flag
-//          wait needs that peer's next flag), so two inbox slots suffice.
+//          and no all-gather.  A rank cannot run two steps ahead of a peer (its next wait needs
+//          that peer's next push), so two inbox slots suffice; a stale pair carries an older tag.
 // A missing peer raises *fault and the CTA leaves W untouched.
+__device__ __forceinline__ void st_pair(uint2 *p, float v, uint32_t tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint2 ld_pair(const uint2 *p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(256)
 p2p_inbox_kernel(P2pPeers peers, const float *__restrict__ deltas, float *W, int64_t n, int rank,
                  int n_ranks, uint32_t *epoch_c, int *fault) {
@@ -154,37 +169,43 @@ p2p_inbox_kernel(P2pPeers peers, const float *__restrict__ deltas, float *W, int
   // until every peer has arrived - fatal when several ranks share one device.
   chain_wait();
   const int c = blockIdx.x;
-  const uint32_t epoch = epoch_c[c];
+  const uint32_t epoch = epoch_c[c], tag = epoch + 1;
   const int slot = epoch & 1;
-  const int64_t n4 = n >> 2;
-  const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
-  const int64_t i0 = c * per, i1 = min(n4, i0 + per);
-  const float4 *src = reinterpret_cast<const float4 *>(deltas);
-  for (int r = 0; r < n_ranks; ++r) {
-    float4 *dst = reinterpret_cast<float4 *>(peers.inbox[r] + ((int64_t)slot * n_ranks + rank) * n);
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = src[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  int ok = 1;
-  if (threadIdx.x < n_ranks) {
-    const size_t word = ((size_t)slot * kXCtas + c) * kMaxP2pRanks;
-    *(volatile uint32_t *)(peers.flags[threadIdx.x] + word + rank) = epoch + 1;
-    ok = spin_until(peers.flags[rank] + word + threadIdx.x, epoch + 1, fault);
-  }
-  __threadfence_system();
-  if (!__syncthreads_and(ok)) return;
-  const float4 *in = reinterpret_cast<const float4 *>(peers.inbox[rank] + (int64_t)slot * n_ranks * n);
-  float4 *w4 = reinterpret_cast<float4 *>(W);
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = c * per, i1 = min(n, i0 + per);
   for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < n_ranks; ++r) {  // rank order: identical sums everywhere
-      const float4 v = __ldcg(in + (int64_t)r * n4 + i);  // written by a peer: not through L1
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const float d = deltas[i];
+    for (int r = 0; r < n_ranks; ++r)
+      st_pair(reinterpret_cast<uint2 *>(peers.inbox[r]) + ((int64_t)slot * n_ranks + rank) * n + i, d, tag);
+  }
+  const uint2 *in = reinterpret_cast<const uint2 *>(peers.inbox[rank]) + (int64_t)slot * n_ranks * n;
+  // wait for every pair of this thread's elements (5 s: a rank is missing)
+  int ok = 1;
+  unsigned long long t0 = 0;
+  for (int64_t i = i0 + threadIdx.x; i < i1 && ok; i += blockDim.x)
+    for (int r = 0; r < n_ranks && ok; ++r) {
+      const uint2 *p = in + (int64_t)r * n + i;
+      unsigned spins = 0;
+      while (ld_pair(p).y != tag) {
+        if ((++spins & 1023u) == 0) {
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t0 == 0) t0 = t1;
+          if (t1 - t0 > 5000000000ull) {
+            *(volatile int *)fault = 1;
+            __threadfence_system();
+            ok = 0;
+            break;
+          }
+        }
+      }
     }
-    float4 w = w4[i];
-    w.x += acc.x; w.y += acc.y; w.z += acc.z; w.w += acc.w;
-    w4[i] = w;
+  if (!__syncthreads_and(ok)) return;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    float acc = 0.0f;
+    for (int r = 0; r < n_ranks; ++r)   // rank order: identical sums everywhere
+      acc += __uint_as_float(ld_pair(in + (int64_t)r * n + i).x);
+    W[i] += acc;
   }
   if (threadIdx.x == 0) epoch_c[c] = epoch + 1;
 }
@@ -194,7 +215,7 @@ p2p_inbox_kernel(P2pPeers peers, const float *__restrict__ deltas, float *W, int
 static int p2p_setup(pb_comm *c, int64_t n) {
   if (c->group) {
     // in-process ranks: the first rank to get here allocates every member's block
-    const size_t bytes = kP2pHeader + sizeof(float) * (size_t)(2 * c->n_ranks * n);
+    const size_t bytes = kP2pHeader + sizeof(uint2) * (size_t)(2 * c->n_ranks * n);
     int dev0 = 0;
     PB_CUDA(cudaGetDevice(&dev0));
     for (pb_comm *m : c->group->members) {
@@ -227,7 +248,7 @@ static int p2p_setup(pb_comm *c, int64_t n) {
   const char *off = getenv("PB_DISABLE_P2P");
   int ok = !(off && off[0] == '1');
   cudaStream_t st = c->ctx->stream;
-  const size_t bytes = kP2pHeader + sizeof(float) * (size_t)(2 * c->n_ranks * n);
+  const size_t bytes = kP2pHeader + sizeof(uint2) * (size_t)(2 * c->n_ranks * n);
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
   if (ok && cudaMalloc(&c->local, bytes) != cudaSuccess) { ok = 0; c->local = nullptr; }
