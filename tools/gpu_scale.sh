@@ -2,7 +2,7 @@
 # bench.py at N = 1, 2, 4, 8 back to back on one 8-GPU box (gpurun --gpus 8 -- bash tools/gpu_scale.sh TAG)
 TAG=${1:-r02e}
 OUT=gpurun_out; mkdir -p $OUT
-for N in 1 2 4 8; do
+for N in ${NS:-1 2 4 8}; do
   if [ $N = 1 ]; then
     timeout 300 python bench.py --steps 20 --warmup 3 --no-other-configs --no-cpu-baseline > $OUT/scale_${TAG}_n$N.json 2> $OUT/scale_${TAG}_n$N.err
   else
@@ -15,7 +15,7 @@ python - <<P
 import json
 base = None
 rows = []
-for n in (1, 2, 4, 8):
+for n in [int(a) for a in "${NS:-1 2 4 8}".split()]:
     try:
         d = json.loads([l for l in open("$OUT/scale_${TAG}_n%d.json" % n) if l.startswith("{")][-1])
     except Exception as e:
