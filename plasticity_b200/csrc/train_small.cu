@@ -10,6 +10,8 @@
 //   forward   ActivationLayer / DenseLayer / SoftmaxLayer   (nnet.h:234-268)
 //   dE/dO     ErrorLayer gradient                            (nnet.h:316-349)
 //   reverse   input_delta with the pre-update weights, then the SGD update (nnet.h:399-460)
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -294,6 +296,147 @@ train_warp_kernel(const SmallNet net, float *__restrict__ W_global, const float 
   }
 }
 
+// ---- register-resident variant: [input activation] (dense, activation) x ND, all <= 32 wide ----
+// The chain above still pays a shared-memory round trip per weight and sample (update ->
+// next sample's product) and a __syncwarp per dense layer.  For the networks the reference's
+// AddDenseLayer chain builds (nnet/circle_test.cc:19-22: Identity input, then dense + activation
+// pairs) every weight lives in REGISTERS, twice: lane o holds row o of W (the product of the
+// forward pass and the update read it: out_o = b_o + sum_i W[o][i] x_i), lane i holds column i
+// (the input gradient reads it: ng_i = sum_o g_o W[o][i]).  Both copies get the same update
+// (w - lr * (g_o * x_i), the same expression, bit-identical), one with x_i broadcast by a
+// shuffle, the other with g_o.  Nothing goes through memory inside a sample; the dependent
+// chain of a sample is shuffle -> FMA chain -> activation per layer.  Same arithmetic and
+// accumulation order as the kernels above.  The input gradient of the first dense layer has no
+// reader in a training loop and is not formed.
+template <class F>
+__device__ __forceinline__ void by_size(int n, F &&f) {
+  if (n <= 4) f(std::integral_constant<int, 4>{});
+  else if (n <= 8) f(std::integral_constant<int, 8>{});
+  else if (n <= 16) f(std::integral_constant<int, 16>{});
+  else f(std::integral_constant<int, 32>{});
+}
+
+template <int ND>
+__global__ void __launch_bounds__(32, 1)
+train_regs_kernel(const SmallNet net, float *__restrict__ W_global, const float *__restrict__ lr_p,
+                  const float *__restrict__ ins, const float *__restrict__ expected,
+                  long long n_samples) {
+  const int lane = threadIdx.x;
+  float wr[ND][32], br[ND], wc[ND][32];
+  int nin[ND], nout[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const int l = 2 * d + 1;
+    nin[d] = net.nin[l];
+    nout[d] = net.nout[l];
+    const float *base = W_global + net.w_off[l];
+    const int ld = nin[d] + 1;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      wr[d][i] = (lane < nout[d] && i < nin[d]) ? base[lane * ld + i] : 0.0f;
+      wc[d][i] = (lane < nin[d] && i < nout[d]) ? base[i * ld + lane] : 0.0f;
+    }
+    br[d] = lane < nout[d] ? base[lane * ld + nin[d]] : 0.0f;
+  }
+  const float lr = lr_p[0];
+  float x_next = 0.0f, e_next = 0.0f;
+  if (n_samples > 0) {
+    if (lane < net.n_in) x_next = ins[lane];
+    if (lane < net.n_out) e_next = expected[lane];
+  }
+  for (long long s = 0; s < n_samples; ++s) {
+    const float x_cur = x_next, e_cur = e_next;
+    if (s + 1 < n_samples) {
+      if (lane < net.n_in) x_next = ins[(s + 1) * net.n_in + lane];
+      if (lane < net.n_out) e_next = expected[(s + 1) * net.n_out + lane];
+    }
+    // ---- forward: a[d] = input of dense layer d, z[d] = its output ----------------------
+    // The loops over a layer's inputs / outputs are unrolled for the next power of two (4, 8,
+    // 16, 32) with predicated bodies: static register indices, no per-iteration branch (a
+    // single warp pays ~15 cycles for every one).
+    float a[ND + 1], z[ND], pz[ND];
+    a[0] = lane < net.n_in ? act_fwd_rt(net.act[0], x_cur) : 0.0f;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      float acc = br[d];
+      by_size(nin[d], [&](auto N) {
+#pragma unroll
+        for (int i = 0; i < decltype(N)::value; ++i) {
+          const float xi = __shfl_sync(kFull, a[d], i);
+          if (i < nin[d]) acc = fmaf(wr[d][i], xi, acc);
+        }
+      });
+      z[d] = acc;
+      const int act = net.act[2 * d + 2];
+      float out;
+      if (act == PB_SIGMOID) {   // p = 2.71828^-z is kept for the derivative (the same value)
+        pz[d] = ref_exp(-acc);
+        out = 1.0f / (1.0f + pz[d]);
+      } else {
+        pz[d] = 0.0f;
+        out = act_fwd_rt(act, acc);
+      }
+      a[d + 1] = lane < nout[d] ? out : 0.0f;
+    }
+    // ---- dE/dO (error_layer.cc:81-91) ------------------------------------------------------
+    float g = 0.0f;
+    if (lane < net.n_out)
+      g = net.loss == PB_MEAN_SQUARED ? a[ND] - e_cur : -1.0f * (e_cur * (1.0f / (a[ND] + kRefEps)));
+    // ---- reverse loop ----------------------------------------------------------------------
+#pragma unroll
+    for (int d = ND - 1; d >= 0; --d) {
+      const int act = net.act[2 * d + 2];
+      float gz;
+      if (act == PB_SIGMOID) {
+        const float q = 1.0f + pz[d];
+        gz = g * (pz[d] / (q * q));
+      } else {
+        gz = act_bwd_rt(act, z[d], g);
+      }
+      g = lane < nout[d] ? gz : 0.0f;   // lane = output o
+      float ng = 0.0f;
+      if (d > 0) {   // with the pre-update weights; lane = input i
+        by_size(nout[d], [&](auto N) {
+#pragma unroll
+          for (int o = 0; o < decltype(N)::value; ++o) {
+            const float go = __shfl_sync(kFull, g, o);
+            if (o < nout[d]) ng = fmaf(go, wc[d][o], ng);
+          }
+        });
+        if (lane >= nin[d]) ng = 0.0f;
+      }
+      const float x_own = lane < nin[d] ? a[d] : 0.0f;
+      by_size(nin[d], [&](auto N) {
+#pragma unroll
+        for (int i = 0; i < decltype(N)::value; ++i) {
+          const float xi = __shfl_sync(kFull, a[d], i);
+          if (i < nin[d]) wr[d][i] = wr[d][i] - lr * (g * xi);
+        }
+      });
+      br[d] = br[d] - lr * g;
+      by_size(nout[d], [&](auto N) {
+#pragma unroll
+        for (int o = 0; o < decltype(N)::value; ++o) {
+          const float go = __shfl_sync(kFull, g, o);
+          if (o < nout[d]) wc[d][o] = wc[d][o] - lr * (go * x_own);
+        }
+      });
+      g = ng;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    float *base = W_global + net.w_off[2 * d + 1];
+    const int ld = nin[d] + 1;
+    if (lane < nout[d]) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nin[d]) base[lane * ld + i] = wr[d][i];
+      base[lane * ld + nin[d]] = br[d];
+    }
+  }
+}
+
 typedef void (*warp_kernel_fn)(const SmallNet, float *, const float *, const float *, const float *,
                                long long);
 warp_kernel_fn warp_kernel_for(int n_layers) {
@@ -349,6 +492,21 @@ int train_loop_small(pb_context *ctx, const pb_layer_desc *layers, int n_layers,
   net.max_io = (int)max_io;
   net.total_out = (int)out_total;
   net.wt_total = (int)wt_total;
+  // Identity/activation input, then (dense, activation) pairs, nothing wider than a warp:
+  // every weight in registers
+  if (max_io <= 32 && (n_layers == 3 || n_layers == 5 || n_layers == 7)) {
+    const char *regs_env = getenv("PB_TRAIN_REGS");
+    bool fits = !(regs_env && regs_env[0] == '0') && net.kind[0] == PB_ACTIVATION;
+    for (int l = 1; l < n_layers && fits; ++l)
+      fits = net.kind[l] == ((l & 1) ? PB_DENSE : PB_ACTIVATION);
+    if (fits) {
+      warp_kernel_fn kern = n_layers == 3 ? train_regs_kernel<1>
+                            : n_layers == 5 ? train_regs_kernel<2> : train_regs_kernel<3>;
+      kern<<<1, 32, 0, ctx->stream>>>(net, weights, lr, d_ins, d_expected, (long long)n_samples);
+      PB_LAUNCHED(ctx);
+      return 0;
+    }
+  }
   // networks no wider than a warp run the one-warp kernel
   if (max_io <= 32) {
     const size_t wsmem = sizeof(float) * (size_t)(wt_total + (n_layers + 1) * 32);

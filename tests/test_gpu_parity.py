@@ -498,6 +498,7 @@ def test_train_loop_one_warp_kernel(ctx, name, monkeypatch):
     {"PB_STEP_CHAIN": "0"},       # no programmatic dependent launches
     {"PB_STEP_FORK": "0"},        # reduce + update kernels on the compute stream
     {"PB_TRAIN_SMALL": "0"},      # per-sample loop as a replayed graph
+    {"PB_TRAIN_REGS": "0"},       # per-sample loop of a small MLP: weights in shared memory
 ], ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
 def test_library_switches(switches):
     """Every environment switch of the library selects a path that is correct on its own:
