@@ -11,9 +11,9 @@
 // normalising in double on the host and converting to float.  A pixel has 256 possible
 // values, so the 256 quotients of a record are formed once (one per thread) and the pixels
 // look theirs up: 256 double divisions per image instead of 3 072 — the kernel shares the
-// GPU with the training step of the previous batch and should stay out of its way (12 -> 6 us
-// with the pixels fetched once as words: the end-to-end rate went from 4.32 M to 4.44 M
-// samples/s at 4.59 M device-resident).
+// GPU with the training step of the previous batch and should stay out of its way (with the
+// pixels fetched once as words instead of twice as bytes the end-to-end rate went from 4.32 M
+// to 4.44 M samples/s, at 4.59 M device-resident).
 #include "common.cuh"
 #include "kernels.cuh"
 
