@@ -54,9 +54,10 @@ struct RCfg {
   static constexpr int N = OC * F;                 // (oc, fy)
   static constexpr int EG = 2;                     // epilogue warps per quadrant
   static constexpr int OPG = OC / EG;              // filters per epilogue warp
-  static constexpr int CPG = OPG * F;              // accumulator columns per epilogue warp
   static constexpr int EPI_WARPS = 4 * EG, MMA_WARP = EPI_WARPS, PROD_WARP0 = EPI_WARPS + 1;
-  static constexpr int THREADS = (EPI_WARPS + 1 + 4) * 32;
+  static constexpr int PQ = 2;                     // A-producer warps per lane quadrant (alternating tiles)
+  static constexpr int PROD_THREADS = 128 * PQ;
+  static constexpr int THREADS = (EPI_WARPS + 1 + 4 * PQ) * 32;
   static constexpr int SP = W + 8;                 // staged row: 4 zeros | W | 4 zeros
   static constexpr int SR = H + F - 1;
   static constexpr int PLANE = SR * SP;
@@ -65,16 +66,15 @@ struct RCfg {
   static constexpr int B_SET = KS * 2 * B_LBO;     // floats of the hi (or lo) filter operand
   static constexpr int SLOT_COLS = KS * 16;        // [k step][hi 8 | lo 8]
   static constexpr int NSLOT = 4;                  // ring of A slots (one tile each)
-  static constexpr int DST = 4;                    // accumulator stages: the MMA -> epilogue -> MMA
-                                                   // hand-offs cost more than a tile's 240 MMA cycles
-  static constexpr int A_COL0 = DST * N;           // accumulator stages first
+  static constexpr int DBUF = BAND * OC;           // accumulator columns of one sample: [row j][oc]
+  static constexpr int A_COL0 = 2 * DBUF;          // two samples' accumulators first
   static constexpr int TMEM_NEED = A_COL0 + NSLOT * SLOT_COLS;
   static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
   static constexpr int K1 = F * F * IC + 1;        // reference filter-block stride
   static constexpr int NWT = OC * K1;
-  static constexpr size_t SMEM = sizeof(float) * (size_t)(2 * IMG + 2 * B_SET + 32) + 8 * (2 * NSLOT + 2 * DST) + 16;
+  static constexpr size_t SMEM = sizeof(float) * (size_t)(2 * IMG + 2 * B_SET + 32) + 8 * (2 * NSLOT + 2 * BAND + 2) + 16;
   static_assert(N % 16 == 0 && N <= 256 && OC % EG == 0 && F == 5, "tile shape");
-  static_assert(CPG == 40, "epilogue column window: two x16 loads and one x8");
+  static_assert(OPG == 8, "an epilogue warp reads its eight filters of a row with one x8 load");
   static_assert(TMEM_NEED <= 512, "tensor-memory budget");
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
@@ -86,6 +86,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&h)[8]
       "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]),
       "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ float tf32_trunc(float x) {
   return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
@@ -112,9 +117,9 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
   float *b_s = img_s + 2 * C::IMG;                                        // hi set, lo set
   float *bias_s = b_s + 2 * C::B_SET;                                     // [32]
   uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 32);
-  uint64_t *a_full = bars, *a_empty = bars + C::NSLOT, *d_full = bars + 2 * C::NSLOT,
-           *d_empty = bars + 2 * C::NSLOT + C::DST;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * C::NSLOT + 2 * C::DST);
+  uint64_t *a_full = bars, *a_empty = bars + C::NSLOT, *row_full = bars + 2 * C::NSLOT,   // [2][BAND]
+           *buf_empty = bars + 2 * C::NSLOT + 2 * C::BAND;                                  // [2]
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * C::NSLOT + 2 * C::BAND + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef PB_ROWS_PROF
@@ -134,7 +139,8 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
   for (int i = tid; i < 2 * C::B_SET; i += C::THREADS) b_s[i] = 0.0f;   // K padding
   if (tid == 0) {
     for (int s = 0; s < C::NSLOT; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < C::DST; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], C::EPI_WARPS); }
+    for (int s = 0; s < 2 * C::BAND; ++s) mbar_init(&row_full[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&buf_empty[s], C::EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == C::MMA_WARP) {
@@ -145,9 +151,20 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (!early_w) chain_wait();
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  if (warp < C::EPI_WARPS) {
+    // every accumulator column starts at zero: all MMAs accumulate (a row's slot is zeroed
+    // again by the warp that reads it out)
+    const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t at = *tmem_ptr + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * C::OPG);
+#pragma unroll 1
+    for (int j = 0; j < 2 * C::BAND; ++j) tmem_st8(at + j * C::OC, zero);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
   {
-    // filters -> K-major no-swizzle operand: row n = (oc, fy), k = (c, fx);
+    // filters -> K-major no-swizzle operand: row n = (4 - fy, oc), k = (c, fx);
     // float(n, k) = (k/4)*B_LBO + (n/8)*32 + (n%8)*4 + k%4.  All L2 loads in flight first.
     constexpr int WL = (C::NWT + C::THREADS - 1) / C::THREADS;
     float wv[WL];
@@ -165,7 +182,7 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
           bias_s[oc] = wv[k];
         } else {
           const int c = r / (C::F * C::F), fy = (r / C::F) % C::F, fx = r % C::F;
-          const int n = oc * C::F + fy, kk = c * C::F + fx;
+          const int n = (C::F - 1 - fy) * C::OC + oc, kk = c * C::F + fx;
           const int at = (kk >> 2) * C::B_LBO + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3);
           const float h = tf32_trunc(wv[k]);
           b_s[at] = h;
@@ -191,26 +208,26 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
       // interior of the padded planes: row y -> staged row y + 2, column x -> x + 4
       float *dst = img_s + st * C::IMG;
       const float *src = In + (int64_t)item * C::IC * C::H * C::W;
-      for (int e = ptid; e < C::IC * C::H * C::W / 4; e += 128) {
+      for (int e = ptid; e < C::IC * C::H * C::W / 4; e += C::PROD_THREADS) {
         const int x4 = e % (C::W / 4), r = e / (C::W / 4);
         const int y = r % C::H, c = r / C::H;
         __pipeline_memcpy_async(dst + c * C::PLANE + (y + C::PAD) * C::SP + 4 + 4 * x4, src + 4 * e, 16);
       }
     };
-    int it = 0, tc = 0;
+    int it = 0;
     if ((int)blockIdx.x < batch) stage(0, blockIdx.x);
     __pipeline_commit();
     for (int item = blockIdx.x; item < batch; item += gridDim.x, ++it) {
       const int st = it & 1;
       // every producer is done reading the other stage (the sample before this one)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS) : "memory");
       if (item + (int)gridDim.x < batch) stage(st ^ 1, item + gridDim.x);
       __pipeline_commit();
       __pipeline_wait_prior(1);
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // everybody's pieces of this sample landed
+      asm volatile("bar.sync 1, %0;" ::"n"(C::PROD_THREADS) : "memory");   // everybody's pieces of this sample landed
       // lane x of quadrant q, tile t: staged row 8q + t, columns x + fx + 2
       const float *row0 = img_s + st * C::IMG + (quad * C::BAND) * C::SP + lane + 2;
-      // the shared-memory loads and the hi/lo split of tile t + 1 run between tile t's
+      // the shared-memory loads and the hi/lo split of the warp's next tile run between a tile's
       // tcgen05.st and the wait for it
       uint32_t hi[C::KS][8], lo[C::KS][8];
       auto prepare = [&](int t) {
@@ -221,9 +238,11 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
           lo[k >> 3][k & 7] = __float_as_uint(x - tf32_trunc(x));
         }
       };
-      prepare(0);
+      const int sub = ptid >> 7;   // the warps of a quadrant alternate over the tiles
+      prepare(sub);
 #pragma unroll 1
-      for (int t = 0; t < C::TILES; ++t, ++tc) {
+      for (int t = sub; t < C::TILES; t += C::PQ) {
+        const int tc = it * C::TILES + t;
         const int slot = tc % C::NSLOT, ph = (tc / C::NSLOT) & 1;
         { PROF_T0
         mbar_wait(&a_empty[slot], ph ^ 1);
@@ -232,7 +251,7 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
         const uint32_t col = tmem_base + lane_base + (uint32_t)(C::A_COL0 + slot * C::SLOT_COLS);
 #pragma unroll
         for (int ks = 0; ks < C::KS; ++ks) tmem_st16(col + ks * 16, hi[ks], lo[ks]);
-        if (t + 1 < C::TILES) prepare(t + 1);
+        if (t + C::PQ < C::TILES) prepare(t + C::PQ);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -246,36 +265,46 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
   } else if (warp == C::MMA_WARP) {
     // ---- MMA issuer -------------------------------------------------------------------
     const bool leader = elect_one();
-    constexpr uint32_t idesc = make_idesc(128, C::N);
     const uint32_t b_hi = smem_u32(b_s) >> 4, b_lo = smem_u32(b_s + C::B_SET) >> 4;
-    int tc = 0;
-    for (int item = blockIdx.x; item < batch; item += gridDim.x) {
-#pragma unroll 1
-      for (int t = 0; t < C::TILES; ++t, ++tc) {
-        const int slot = tc % C::NSLOT, aph = (tc / C::NSLOT) & 1;
-        const int ds = tc % C::DST, dph = (tc / C::DST) & 1;
-        { PROF_T0
-        mbar_wait(&d_empty[ds], dph ^ 1);
-        PROF_ADD(0) }
+    int it = 0;
+    static_assert(C::TILES % C::NSLOT == 0, "a sample's tiles use the A slots in a fixed pattern");
+    for (int item = blockIdx.x; item < batch; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      { PROF_T0
+      mbar_wait(&buf_empty[buf], ((it >> 1) & 1) ^ 1);   // its rows of two samples ago are read out
+      PROF_ADD(0) }
+      // unrolled over the twelve tiles: window, instruction descriptor and operand offsets of a
+      // tile are immediates - with six MMAs per tile the issuing thread's own instruction
+      // stream, not the tensor pipe, sets the pace
+#pragma unroll
+      for (int t = 0; t < C::TILES; ++t) {
+        const int slot = t % C::NSLOT, aph = (it * (C::TILES / C::NSLOT) + t / C::NSLOT) & 1;
         { PROF_T0
         mbar_wait(&a_full[slot], aph);
         PROF_ADD(1) }
         tc_fence_after();
+        // input row t feeds output rows j = t-4 .. t (fy = t - j) that lie inside the band:
+        // a window of the accumulator [row j][oc] and the matching blocks of the filter operand
+        const int j0 = max(0, t - (C::F - 1)), j1 = min(C::BAND - 1, t);
+        const int i0 = max(0, (C::F - 1) - t);
+        const int n_cols = (j1 - j0 + 1) * C::OC;
         if (leader) {
-          const uint32_t d = tmem_base + (uint32_t)(ds * C::N);
+          const uint32_t idesc = make_idesc(128, n_cols);
+          const uint32_t d = tmem_base + (uint32_t)(buf * C::DBUF + j0 * C::OC);
           const uint32_t a_col = tmem_base + (uint32_t)(C::A_COL0 + slot * C::SLOT_COLS);
+          const uint32_t b_off = (uint32_t)(i0 * C::OC * 4 / 4);   // 16-byte units: OC rows of 16 B
 #pragma unroll
           for (int ks = 0; ks < C::KS; ++ks) {
             // LBO = one 4-wide K chunk (N rows of 16 B), SBO = 8 rows (128 B)
-            const uint64_t bh = smem_desc(b_hi + (uint32_t)(ks * 2 * C::B_LBO / 4), C::B_LBO / 4, 8);
-            const uint64_t bl = smem_desc(b_lo + (uint32_t)(ks * 2 * C::B_LBO / 4), C::B_LBO / 4, 8);
+            const uint64_t bh = smem_desc(b_hi + b_off + (uint32_t)(ks * 2 * C::B_LBO / 4), C::B_LBO / 4, 8);
+            const uint64_t bl = smem_desc(b_lo + b_off + (uint32_t)(ks * 2 * C::B_LBO / 4), C::B_LBO / 4, 8);
             const uint32_t ah = a_col + ks * 16, al = ah + 8;
-            umma_tf32_ts(d, ah, bh, idesc, ks > 0);
+            umma_tf32_ts(d, ah, bh, idesc, 1);
             umma_tf32_ts(d, al, bh, idesc, 1);
             umma_tf32_ts(d, ah, bl, idesc, 1);
           }
           umma_commit(&a_empty[slot]);
-          umma_commit(&d_full[ds]);
+          if (t >= C::F - 1) umma_commit(&row_full[buf * C::BAND + t - (C::F - 1)]);
         }
         __syncwarp();
       }
@@ -286,74 +315,60 @@ conv_rows_kernel(const float *__restrict__ In, const float *__restrict__ Wt, flo
   } else {
     // ---- epilogue: rolling sums over the tiles of a band ---------------------------------
     const int quad = warp & 3, grp = warp >> 2;
-    const uint32_t d_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * C::CPG);
+    const uint32_t d_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * C::OPG);
     float bias[C::OPG];
 #pragma unroll
     for (int o = 0; o < C::OPG; ++o) bias[o] = bias_s[grp * C::OPG + o];
-    int tc = 0;
-    for (int item = blockIdx.x; item < batch; item += gridDim.x) {
-      // row j = t - 4 of the band, the one tile t completes
-      float *out = Out + (((int64_t)item * C::OC + grp * C::OPG) * C::H + quad * C::BAND - (C::F - 1)) * C::W + lane;
-      float *out2 = Out2 + (((int64_t)item * C::OC + grp * C::OPG) * (C::H / 2) + quad * (C::BAND / 2) - (C::F - 1) / 2) *
-                               (C::W / 2) + (lane >> 1) + ((lane & 1) ? (C::OPG / 2) * (C::H / 2) * (C::W / 2) : 0);
-      // w[fy][o]: the sum so far of row t - fy.  A tile moves every row one slot down with the
-      // add itself (w[fy+1] = w[fy] + column fy+1), so the loop stays rolled - unrolled over
-      // the twelve tiles the compiler hoists the loads of four tiles and spills.  Rows that
-      // start before the band or do not finish inside it collect garbage and are never stored.
-      float w[C::F - 1][C::OPG], prev[C::OPG];
+    const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int it = 0;
+    for (int item = blockIdx.x; item < batch; item += gridDim.x, ++it) {
+      const int buf = it & 1, par = (it >> 1) & 1;
+      float *out = Out + (((int64_t)item * C::OC + grp * C::OPG) * C::H + quad * C::BAND) * C::W + lane;
+      float *out2 = Out2 + (((int64_t)item * C::OC + grp * C::OPG) * (C::H / 2) + quad * (C::BAND / 2)) * (C::W / 2) +
+                    (lane >> 1) + ((lane & 1) ? (C::OPG / 2) * (C::H / 2) * (C::W / 2) : 0);
+      float prev[C::OPG];
 #pragma unroll
-      for (int o = 0; o < C::OPG; ++o) {
-        prev[o] = 0.0f;
-#pragma unroll
-        for (int fy = 0; fy < C::F - 1; ++fy) w[fy][o] = 0.0f;
-      }
+      for (int o = 0; o < C::OPG; ++o) prev[o] = 0.0f;
 #pragma unroll 1
-      for (int t = 0; t < C::TILES; ++t, ++tc) {
-        const int ds = tc % C::DST, dph = (tc / C::DST) & 1;
+      for (int j = 0; j < C::BAND; ++j) {
         { PROF_T0
-        mbar_wait(&d_full[ds], dph);
+        mbar_wait(&row_full[buf * C::BAND + j], par);   // tile j + 4, the row's last, is done
         PROF_ADD(0) }
         tc_fence_after();
-        float v[C::CPG];
-        tmem_ld16(d_addr + ds * C::N, v);
-        tmem_ld16(d_addr + ds * C::N + 16, v + 16);
-        tmem_ld8(d_addr + ds * C::N + 32, v + 32);
+        float v[C::OPG];
+        const uint32_t at = d_addr + (uint32_t)(buf * C::DBUF + j * C::OC);
+        tmem_ld8(at, v);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&d_empty[ds]);
+        tmem_st8(at, zero);   // the slot of row j of the sample after next
         float done[C::OPG];
 #pragma unroll
         for (int o = 0; o < C::OPG; ++o) {
-          done[o] = w[3][o] + v[o * C::F + 4];
-          w[3][o] = w[2][o] + v[o * C::F + 3];
-          w[2][o] = w[1][o] + v[o * C::F + 2];
-          w[1][o] = w[0][o] + v[o * C::F + 1];
-          w[0][o] = bias[o] + v[o * C::F];
+          done[o] = v[o] + bias[o];
+          out[(o * C::H + j) * C::W] = done[o];
         }
-        if (t >= C::F - 1) {
+        if constexpr (ACT >= 0) {
+          if (j & 1) {   // the second row of a pool window
+            // the two lanes of a window split the filters: the even lane finishes filters
+            // 0 .. OPG/2-1, the odd lane the other half - one exchange per filter PAIR and
+            // half the activations per lane
+            const bool odd = lane & 1;
 #pragma unroll
-          for (int o = 0; o < C::OPG; ++o) out[(o * C::H + t) * C::W] = done[o];
-          if constexpr (ACT >= 0) {
-            if (t & 1) {   // t - 4 odd: the second row of a pool window
-              // the two lanes of a window split the filters: the even lane finishes filters
-              // 0 .. OPG/2-1, the odd lane the other half - one exchange per filter PAIR and
-              // half the activations per lane
-              const bool odd = lane & 1;
-#pragma unroll
-              for (int o = 0; o < C::OPG / 2; ++o) {
-                const float m0 = fmaxf(prev[o], done[o]);
-                const float m1 = fmaxf(prev[o + C::OPG / 2], done[o + C::OPG / 2]);
-                const float theirs = __shfl_xor_sync(0xffffffffu, odd ? m0 : m1, 1);
-                const float p = act_fwd<(ACT >= 0 ? ACT : 0)>(fmaxf(odd ? m1 : m0, theirs));
-                out2[(o * (C::H / 2) + (t >> 1)) * (C::W / 2)] = p;
-              }
+            for (int o = 0; o < C::OPG / 2; ++o) {
+              const float m0 = fmaxf(prev[o], done[o]);
+              const float m1 = fmaxf(prev[o + C::OPG / 2], done[o + C::OPG / 2]);
+              const float theirs = __shfl_xor_sync(0xffffffffu, odd ? m0 : m1, 1);
+              const float p = act_fwd<(ACT >= 0 ? ACT : 0)>(fmaxf(odd ? m1 : m0, theirs));
+              out2[(o * (C::H / 2) + (j >> 1)) * (C::W / 2)] = p;
             }
           }
         }
 #pragma unroll
         for (int o = 0; o < C::OPG; ++o) prev[o] = done[o];
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&buf_empty[buf]);
     }
   }
 
