@@ -1,38 +1,44 @@
 // 3xTF32 tcgen05 forward convolution for the network's FIRST layer (3 input channels, 16
 // filters, 32x32 images, 5x5 stride-1 "same": nnet/cifar_test.cc:293-300; semantics
-// nnet/convolution_layer.cc:50-131) with the IMAGE in tensor memory and the fy taps moved out of
-// the contraction:
+// nnet/convolution_layer.cc:50-131) with the IMAGE in tensor memory and the fy taps summed by the
+// tensor core over TILES:
 //
 //   A[(q,x)][(c,fx)]   = Ipad[c][8q + t][x + fx]      tile t, lane = (row band q, column x)
-//   B[(oc,fy)][(c,fx)] = Wk[oc,c,fy,fx]               80 x 16 (15 used), shared memory, static
-//   D_t[(q,x)][(oc,fy)] = A * B^T                      one image row per lane quadrant
-//   Out[oc][8q + j][x] = bias_oc + sum_fy D_{j+fy}[(q,x)][(oc,fy)]
+//   B[(4-fy,oc)][(c,fx)] = Wk[oc,c,fy,fx]             80 x 16 (15 used), shared memory, static
+//   D[(q,x)][(j,oc)]  += A_t * B[fy = t - j]^T         for the rows j = t-4 .. t inside the band
+//   Out[oc][8q + j][x] = bias_oc + D[(q,x)][(j,oc)]    once tile j + 4 is done
 //
 // With 3 input channels every other mapping leaves the tensor core a sliver: pixels x (16
 // filters) with the 75 taps as K is bound by fetching the 128-row image operand from shared
 // memory for 16 columns of work (conv_umma.cu, 43 us), filters x pixels with (fy,c) as K folds
 // five accumulator rows per output across lanes (conv_wt_umma.cu, 50 us).  Here
 //  * a lane quadrant owns a BAND of eight output rows and walks the twelve padded input rows
-//    that feed it, one per tile: the fy sum runs over TILES, i.e. over time in the same lane, so
-//    the epilogue folds it with register adds - no shuffle, no staging - and stores whole
-//    128-byte image rows;
+//    that feed it, one per tile.  The accumulator of a sample is [output row j][filter] = 128
+//    columns; input row t contributes to the rows j = t-4 .. t with the filter rows fy = t - j,
+//    i.e. to a WINDOW of the accumulator that slides by one row (16 columns) per tile, against
+//    a FIXED filter operand ordered (4 - fy, oc): one MMA per K step with D's address = the
+//    window start, N = 16 x (rows of the window inside the band) = 16 .. 80.  The fy sum is
+//    the MMA's own accumulation - the epilogue of the first version read 80 columns per tile and
+//    added them in registers (40 adds per warp and tile, the kernel's bound);
+//  * a row is complete when tile j + 4 is done: the epilogue reads its 16 columns (one x8 load
+//    per warp), adds the bias, stores whole 128-byte image rows and writes zeros back - every MMA
+//    accumulates, a slot is clean again long before the sample after next reaches it (two
+//    accumulator buffers);
 //  * the A operand (the 5 fx shifts of 3 channels of one image row, hi and lo) is written to
-//    tensor memory with tcgen05.st by the warp that owns the quadrant - 15 conflict-free
-//    shared-memory loads per lane and tile, no operand fetch by the MMA;
-//  * N = 80 columns per MMA (40 cycles at the tensor rate, above the ~22 cycle issue floor), six
-//    MMAs per tile = four image rows: 2880 MMA cycles per image.
+//    tensor memory with tcgen05.st by the warps that own the quadrant (two, alternating tiles)
+//    - 15 conflict-free shared-memory loads per lane and tile, no operand fetch by the MMA;
+//  * six MMAs per tile, 2 160 MMA cycles per sample; the MMA warp's tile loop is unrolled (window,
+//    instruction descriptor and operand offsets are immediates): with so few MMAs per tile the
+//    issuing thread's own instruction stream sets the pace, not the tensor pipe.
 // The 12/8 halo redundancy (rows shared by neighbouring bands are multiplied twice) is the price.
 //
-// Warp roles (416 threads, one persistent CTA per SM, one item = one sample):
-//   warps 0-7    epilogue: lane quadrant = warp & 3, filters 8*(warp >> 2) .. +7 (40 accumulator
-//                columns): rolling sums of the band's rows, bias, store; with ACT >= 0 also the
-//                2x2 max-pool of act(conv output) (one lane-pair shuffle per filter and row pair).
-//                The kernel is bound by instruction issue, not by the 240 MMA cycles of a tile:
-//                two warps per quadrant amortise the per-tile hand-off (wait, fences, arrive) over
-//                twice the columns of four, and 13 warps leave 128 registers per thread (no spills)
+// Warp roles (544 threads, one persistent CTA per SM, one item = one sample):
+//   warps 0-7    epilogue: lane quadrant = warp & 3, filters 8*(warp >> 2) .. +7: bias, store; with
+//                ACT >= 0 also the 2x2 max-pool of act(conv output) (the two lanes of a window split
+//                the filters: one exchange per filter pair)
 //   warp  8      MMA issuer, tensor-memory allocator
-//   warps 9-12   A producers (quadrant = warp & 3); together they also stage the samples
-//                (cp.async, two stages)
+//   warps 9-16   A producers (quadrant = warp & 3, tiles alternate between the two warps of a
+//                quadrant); together they also stage the samples (cp.async, two stages)
 #include <cuda_pipeline.h>
 
 #include "common.cuh"
