@@ -277,6 +277,32 @@ def test_batch_train_fused_plan_odd_batches(ctx, B):
     util.assert_close(util.read_product_weights(net, S), w_ref, f"B={B} weights (in-place step)")
 
 
+@pytest.mark.parametrize("act", ["sigmoid", "identity"])
+def test_batch_train_fused_plan_other_activations(ctx, act):
+    """The fused tensor-core kernels are instantiated per activation (fused pool epilogue of the
+    forward kernels, pool/activation-backward producers of the input-gradient kernels, gradient
+    formers of the first layer's weight gradient); the CIFAR network only uses LeakyReLU.  The
+    same network with sigmoid / identity behind every convolution (ReLU ties every all-negative
+    pool window at zero, which the margin-filtered draw cannot avoid), one gradient-sum step
+    at the smallest batch that takes the tensor-core kernels, against the restated oracle."""
+    spec = po.spec_text("cifar").replace(" leaky", " " + act)
+    S = po.RestatedNet(spec)
+    model, loss = util.architecture_from_spec(spec)
+    rng = np.random.default_rng(9100 + len(act))
+    w0 = util.xavier_like(S, rng)
+    B, lr = 64, 0.002
+    es = util.f32(rng.uniform(0, 1, (B, S.n_out)))
+    xs = util.draw_with_pool_margin(S, rng, B, w0)
+    net = pb.Nnet(model, pb.NoWeightInit, loss, max_batch=B)
+    net.SetLearningParameters(pb.Nnet.LearningParameters(lr))
+    util.load_product_weights(net, S, w0)
+    w_ref = w0.copy()
+    S.batch_train(xs.copy(), es.copy(), w_ref, lr)
+    util.assert_close(util.device_deltas(net, S, xs, es), w_ref - w0, f"{act}: deltas (delta-buffer pass)")
+    net.BatchTrain(net.MakeBuffer(xs.reshape(-1)), net.MakeBuffer(es.reshape(-1)), B)
+    util.assert_close(util.read_product_weights(net, S), w_ref, f"{act}: weights (in-place step)")
+
+
 @pytest.mark.parametrize("layer", [1, 4, 7])
 def test_conv_persistent_pipeline_large_batch(ctx, layer):
     """The tensor-core convolution kernels are persistent (one CTA per SM walking
