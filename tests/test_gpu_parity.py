@@ -277,13 +277,12 @@ def test_batch_train_fused_plan_odd_batches(ctx, B):
     util.assert_close(util.read_product_weights(net, S), w_ref, f"B={B} weights (in-place step)")
 
 
-@pytest.mark.parametrize("act", ["sigmoid", "identity"])
+@pytest.mark.parametrize("act", ["relu", "sigmoid", "identity"])
 def test_batch_train_fused_plan_other_activations(ctx, act):
     """The fused tensor-core kernels are instantiated per activation (fused pool epilogue of the
     forward kernels, pool/activation-backward producers of the input-gradient kernels, gradient
     formers of the first layer's weight gradient); the CIFAR network only uses LeakyReLU.  The
-    same network with sigmoid / identity behind every convolution (ReLU ties every all-negative
-    pool window at zero, which the margin-filtered draw cannot avoid), one gradient-sum step
+    same network with ReLU / sigmoid / identity behind every convolution, one gradient-sum step
     at the smallest batch that takes the tensor-core kernels, against the restated oracle."""
     spec = po.spec_text("cifar").replace(" leaky", " " + act)
     S = po.RestatedNet(spec)

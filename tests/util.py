@@ -110,6 +110,17 @@ def pool_margin(onet, x, weights):
         win = np.sort(v.transpose(0, 1, 3, 2, 4).reshape(-1, gh * gw), axis=1)
         if win.shape[1] < 2:
             continue
+        prev = onet.layers[l - 1] if l > 0 else None
+        if prev is not None and prev.kind == po.KINDS["act"] and prev.act == po.ACTS["relu"]:
+            # a window that ReLU flattened to zeros routes to every element, but every one of
+            # them has derivative 0: harmless.  A window whose maximum is barely positive is
+            # not: its sign can differ in fp32.
+            live = win[:, -1] > 0
+            if np.any(live & (win[:, -1] <= 1e-4)):
+                return 0.0
+            win = win[live]
+            if win.shape[0] == 0:
+                continue
         gap = (win[:, -1] - win[:, -2]) / (np.abs(win[:, -1]) + 1e-3)
         worst = min(worst, float(gap.min()))
     return worst
@@ -119,7 +130,12 @@ def draw_with_pool_margin(onet, rng, n, weights, margin=2e-5, scale=1.0):
     """n fp32-representable N(0, scale^2) samples whose pool windows all have a
     top-2 gap of at least `margin` (relative) under `weights`."""
     out = []
+    tries = 0
     while len(out) < n:
+        tries += 1
+        if tries > 200 * n + 1000:
+            raise RuntimeError("draw_with_pool_margin: no sample with a pool margin in "
+                               f"{tries} draws (a network whose windows always tie?)")
         x = f32(rng.normal(0, scale, onet.n_in))
         if pool_margin(onet, x, weights) >= margin:
             out.append(x)
